@@ -1,0 +1,135 @@
+/*
+ * nbc.h -- C-ABI of libnbc.so: the B200 (sm_100a) segmentation hot path of NeuralBarkCalculator.
+ *
+ * The reference (TortillasAlfred/NeuralBarkCalculator) is pure Python and has no FFI; the functions below are
+ * what a ctypes binding for its hot path binds.  Each entry cites the reference code it
+ * replaces as  file:line  relative to  src/bark_calculator/ .
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in _host; the caller allocates everything
+ *    (the library owns only the opaque nbc_plan and its packed-weight cache);
+ *  - every launch function takes the CUDA stream (a cudaStream_t passed as void*) and is asynchronous;
+ *  - every function returns 0 on success or a negative nbc_status; nbc_last_error() gives the text
+ *    (thread-local).  There is NO CPU fallback: a missing GPU or a non-sm_100 device is an error.
+ *  - activations are NHWC bf16, masks are u8 [N,H,W], logits are f32 planar [N,3,h,w].
+ */
+#ifndef NBC_H_
+#define NBC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  NBC_OK = 0,
+  NBC_ERR_INVALID = -1,      /* bad argument / unsupported shape */
+  NBC_ERR_CUDA = -2,         /* CUDA runtime / driver error */
+  NBC_ERR_DEVICE = -3,       /* no CUDA device or not compute capability 10.x */
+  NBC_ERR_WORKSPACE = -4,    /* workspace too small */
+  NBC_ERR_KERNEL = -5        /* a kernel reported an internal error (pipeline timeout) */
+} nbc_status;
+
+typedef struct nbc_plan nbc_plan;
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+int nbc_version(void);
+const char* nbc_last_error(void);
+/* checks that `device` exists and is sm_100 (B200); must succeed before anything else is called */
+int nbc_device_check(int device);
+/* number of kernels launched by this library in this process since load (bench.py "gpu_launches") */
+int64_t nbc_launch_count(void);
+
+/* ---- K1: 4x cubic resize + dark-band trim  (models.py:157-166 trim_black, 191-203 _preprocess_image) ------
+ * raw: H x W x 3 u8 with `pitch` bytes per row.  flags: bit0 = channels are BGR, bit1 = rows are bottom-up
+ * (a 24-bit BMP pixel array is flags=3), so the BMP is consumed without a host-side decode.
+ * Requires H % 4 == 0 and W % 4 == 0 (the 4096^2 -> 1024^2 scan case).  Writes the trimmed image, rows
+ * [first,last) of the resized one, contiguously to out (capacity (H/4)*(W/4)*3) and {first,last} to
+ * first_last (2 x int32).  Trimming is applied only when the resized image is square (models.py:200). */
+size_t nbc_preprocess_workspace_bytes(int H, int W);
+int nbc_preprocess_4x_u8(const uint8_t* raw, int H, int W, int64_t pitch, int flags, uint8_t* out,
+                         int32_t* first_last, void* workspace, size_t workspace_bytes, void* stream);
+/* trim only, for images that need no resize (max dim <= 1024, models.py:194,200) */
+int nbc_trim_u8(const uint8_t* img, int H, int W, uint8_t* out, int32_t* first_last, void* workspace,
+                size_t workspace_bytes, void* stream);
+
+/* ---- weights: BatchNorm folding + packing  (models.py:113-139; eval-mode BN of torchvision resnet50) --------
+ * w: f32 OIHW [Cout,Cin,kh,kw].  gamma/beta/mean/var may be NULL (no BN: scale 1, shift = conv_bias or 0).
+ * Output: bf16 [Cout][kh][kw][cin_pad] with w * gamma/sqrt(var+eps) folded in (channels >= Cin zero), and
+ * f32 bias[Cout] = beta - mean*gamma/sqrt(var+eps) (+ conv_bias * scale). */
+int nbc_fold_bn_pack(const float* w, const float* gamma, const float* beta, const float* mean, const float* var,
+                     const float* conv_bias, float eps, int Cout, int Cin, int kh, int kw, int cin_pad,
+                     void* w_packed_bf16, float* bias_out, void* stream);
+
+/* ---- K2: one convolution layer, implicit GEMM  (every nn.Conv2d+BN(+ReLU)(+residual) of models.py:127-139) --
+ * y[N,Ho,Wo,Cout] = act( conv(x[N,H,W,Cin], w) + bias (+ residual[N,Ho,Wo,Cout]) ), bf16 NHWC, f32 accumulate.
+ * impl: 0 = auto (tcgen05 when the shape allows), 1 = tcgen05/TMEM/TMA kernel, 2 = mma.sync kernel. */
+typedef struct {
+  int32_t N, H, W, Cin, Cout;
+  int32_t kh, kw, stride, pad, dil;
+  int32_t relu;
+  int32_t impl;
+} nbc_conv_desc;
+int nbc_conv_bf16(const nbc_conv_desc* desc, const void* x, const void* w_packed, const float* bias,
+                  const void* residual, void* y, void* stream);
+
+/* ---- stem: ToTensor + Normalize + conv1 7x7/2 + bn1 + relu, then maxpool 3x3/2
+ *      (dataset.py:181-190, models.py:233-237, torchvision resnet50 stem) ---------------------------------------
+ * img: u8 NHWC [N,H,W,3]; w_stem: f32 [64][7][7][3] BN-folded; out: bf16 NHWC [N,ceil(H/2),ceil(W/2),64]. */
+int nbc_stem_u8(const uint8_t* img, int N, int H, int W, const float* mean3_host, const float* std3_host,
+                const float* w_stem, const float* bias, void* out, void* stream);
+/* same conv on an already normalised f32 NCHW tensor [N,3,H,W] (what nn.Module.forward receives, models.py:33) */
+int nbc_stem_f32(const float* x_nchw, int N, int H, int W, const float* w_stem, const float* bias, void* out,
+                 void* stream);
+int nbc_maxpool3x3s2_bf16(const void* x, int N, int H, int W, int C, void* y, void* stream);
+
+/* ---- head tail: Dropout(eval)=identity + Conv2d(512,3,1)+bias  (models.py:113-124) -> f32 planar logits ------ */
+int nbc_head_1x1(const void* x_bf16, int64_t pixels_per_image, int N, int Cin, const float* w3xC, const float* bias3,
+                 float* logits_planar, void* stream);
+
+/* ---- K3: bicubic upsample (A=-0.75, align_corners=False) + argmax  (models.py:38-41, 270) -----------------------
+ * logits: f32 [N,3,h,w] -> mask u8 [N,H,W] (ties -> lowest class).  nbc_upsample_bicubic writes the f32
+ * [N,3,H,W] logits instead (what SimpleSegmentationModel.forward returns). */
+int nbc_upsample_argmax(const float* logits, int N, int h, int w, int H, int W, uint8_t* mask, void* stream);
+int nbc_upsample_bicubic(const float* logits, int N, int C, int h, int w, int H, int W, float* out, void* stream);
+
+/* ---- K5: small-region removal + class counts  (utils.py:135-148, models.py:273-276, 323-332) ------------------
+ * mask u8 [N,H,W] in place; 8-connected; regions with size < threshold are flipped (two-stage).
+ * exclude_nodes != 0 rewrites class 2 -> 1 afterwards.  counts: int32 [N,3] pixels per class of the result. */
+size_t nbc_ccl_workspace_bytes(int N, int H, int W);
+int nbc_remove_small_zones(uint8_t* mask, int N, int H, int W, int threshold, int exclude_nodes, int32_t* counts,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K4: max-of-class-index weighted cross entropy, forward + backward  (utils.py:151-165) ----------------------
+ * logits f32 [N,3,H,W]; target u8 [N,H,W] (target_is_i64: int64); weights f32[3].  loss: f32 scalar (mean over
+ * N*H*W); grad (may be NULL): d loss / d logits, f32 [N,3,H,W].  Deterministic two-stage reduction. */
+size_t nbc_wce_workspace_bytes(int N, int H, int W);
+int nbc_wce_fwd_bwd(const float* logits, const void* target, int target_is_i64, const float* weights3, int N, int H,
+                    int W, float* loss, float* grad, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- the whole network  (models.py:27-43 SimpleSegmentationModel.forward, 127-139 fcn_resnet50) ------------------
+ * tensors_host: host array of DEVICE pointers to the 326 f32 state_dict tensors in torchvision key order
+ * (backbone.conv1.weight, backbone.bn1.{weight,bias,running_mean,running_var,num_batches_tracked}, ...).
+ * The plan folds BN, packs bf16 weights (owned by the plan) and keeps nothing else. */
+nbc_plan* nbc_plan_create(const void* const* tensors_host, int n_tensors, const float* mean3_host,
+                          const float* std3_host);
+void nbc_plan_destroy(nbc_plan* plan);
+size_t nbc_plan_workspace_bytes(const nbc_plan* plan, int N, int H, int W);
+/* input_kind 0: images u8 NHWC [N,H,W,3] (normalised inside with the plan's mean/std);
+ * input_kind 1: f32 NCHW [N,3,H,W] already normalised.  -> lowres_logits f32 [N,3,ceil(H/8),ceil(W/8)] */
+int nbc_plan_forward(nbc_plan* plan, const void* input, int input_kind, int N, int H, int W, float* lowres_logits,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* per-layer timing of the last shape (debug / profiling): runs the forward with events around every layer;
+ * ms_out[n_layers] and flops_out[n_layers] (may be NULL); returns number of layers or <0 */
+int nbc_plan_profile(nbc_plan* plan, const void* input, int input_kind, int N, int H, int W, float* lowres_logits,
+                     void* workspace, size_t workspace_bytes, void* stream, float* ms_out, double* flops_out,
+                     int max_layers);
+/* conv implementation used by the plan: 0 auto, 1 force tcgen05 where legal, 2 force mma.sync */
+int nbc_plan_set_impl(nbc_plan* plan, int impl);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBC_H_ */

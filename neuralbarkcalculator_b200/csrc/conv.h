@@ -1,0 +1,40 @@
+// Internal convolution interfaces shared by conv_tc.cu (tcgen05), conv_mma.cu (mma.sync), plan.cu and api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <stdint.h>
+#include <string.h>
+
+namespace nbc {
+
+struct ConvGeom {
+  int N, H, W, Cin, Cout;
+  int kh, kw, stride, pad, dil;
+  int relu;
+  int Ho() const { return (H + 2 * pad - dil * (kh - 1) - 1) / stride + 1; }
+  int Wo() const { return (W + 2 * pad - dil * (kw - 1) - 1) / stride + 1; }
+  double flops() const { return 2.0 * N * Ho() * Wo() * (double)Cout * Cin * kh * kw; }
+};
+
+// tcgen05 path: tensor maps are encoded once per (shape, pointers) and reused across launches
+struct ConvTcPrepared {
+  alignas(64) unsigned char storage[1024];
+};
+bool conv_tc_supported(const ConvGeom& g);
+int conv_tc_prepare(const ConvGeom& g, const void* x, const void* w, const float* bias, const void* residual, void* y,
+                    ConvTcPrepared* out);
+int conv_tc_run(const ConvTcPrepared* prep, cudaStream_t stream);
+int conv_tc(const ConvGeom& g, const void* x, const void* w, const float* bias, const void* residual, void* y,
+            cudaStream_t stream);
+
+// mma.sync path (any stride / dilation / kernel size; Cin % 32 == 0, Cout % 64 == 0)
+bool conv_mma_supported(const ConvGeom& g);
+int conv_mma(const ConvGeom& g, const void* x, const void* w, const float* bias, const void* residual, void* y,
+             cudaStream_t stream);
+
+// BN fold + pack (api.cu): w f32 OIHW -> bf16 (and/or f32) [Cout][kh][kw][cin_pad], bias f32[Cout]
+int fold_pack(const float* w, const float* gamma, const float* beta, const float* mean, const float* var,
+              const float* cb, float eps, int Cout, int Cin, int kh, int kw, int cin_pad, void* wp_bf16, float* wp_f32,
+              float* bias, cudaStream_t stream);
+
+}  // namespace nbc

@@ -1,0 +1,401 @@
+// K2 -- implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA operands).
+//
+// Replaces every nn.Conv2d + BatchNorm2d (+ReLU, +residual add) of the reference's FCN-ResNet50
+// (models.py:113-139 FCNHead / fcn_resnet50; torchvision Bottleneck) for Cin % 64 == 0, Cout % 64 == 0.
+//
+// GEMM view:  D[M = N*Ho*Wo pixels, Cout] = A[M, K = taps*Cin] * W[Cout, K]^T   (bf16 x bf16 -> f32)
+//   * M tile  = a th x tw rectangle of 128 output pixels of one image.  For tap (ky,kx) and channel block c the A
+//     operand is ONE 4-D TMA box {64 ch, tw, th, 1} of the NHWC input shifted by the tap offset; out-of-bounds
+//     coordinates (the conv zero padding, ragged image edges) are zero-filled by the TMA unit.
+//   * stride-2 convs read one of four "parity lattices" of the input (tensor maps with doubled strides), so the
+//     box stays dense; the tap table says which lattice and which shift.
+//   * B operand = TMA box {64 k, BLOCK_N} of the packed weights [Cout][kh][kw][Cin] (BN scale folded in).
+//   * both land in 128B-swizzled K-major smem and are consumed by tcgen05.mma (M=128, N=BLOCK_N, K=16) issued
+//     by one thread; the f32 accumulator lives in TMEM, double buffered so the epilogue of tile i overlaps the
+//     main loop of tile i+1.
+//   * epilogue (4 warps): tcgen05.ld -> + bias (+ residual) -> ReLU -> bf16 -> 64 B vector stores.
+// Persistent CTAs (one per SM), warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue.
+#include "common.cuh"
+#include "conv.h"
+
+namespace nbc {
+
+struct ConvTcParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* out;
+  int N, Ho, Wo, Cout;
+  int tw_log2, th, tw, tiles_w, tiles_h;
+  int num_m_tiles, num_n_tiles;
+  int n_taps, cblocks;
+  int relu;
+  int8_t tap_map[9];
+  int16_t tap_dh[9];
+  int16_t tap_dw[9];
+};
+
+constexpr int kTcThreads = 192;
+constexpr int kABytes = 128 * 128;  // 128 pixels x 64 bf16
+
+template <int BN>
+struct TcCfg {
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tfull_bar = empty_bar + Cfg::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmB);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int kblocks = p.n_taps * p.cblocks;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.num_n_tiles;
+        int m_tile = tile / p.num_n_tiles;
+        const int tw_i = m_tile % p.tiles_w;
+        m_tile /= p.tiles_w;
+        const int th_i = m_tile % p.tiles_h;
+        const int img = m_tile / p.tiles_h;
+        const int w0 = tw_i << p.tw_log2, h0 = th_i * p.th, n0 = n_tile * BN;
+        for (int tap = 0; tap < p.n_taps; ++tap) {
+          const CUtensorMap* mA = &p.tmA[p.tap_map[tap]];
+          const int cw = w0 + p.tap_dw[tap], ch = h0 + p.tap_dh[tap];
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + (int)stage);
+            uint8_t* sA = smem + stage * Cfg::kStageBytes;
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_4d(sA, mA, &full_bar[stage], cb * 64, cw, ch, img);
+            tma_load_2d(sA + kABytes, &p.tmB, &full_bar[stage], (tap * p.cblocks + cb) * 64, n0);
+            if (++stage == Cfg::kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 300 + (int)acc);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 200 + (int)stage);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                      (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================ epilogue (warps 2..5) ================================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int hl = row >> p.tw_log2, wl = row & (p.tw - 1);
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.num_n_tiles;
+      int m_tile = tile / p.num_n_tiles;
+      const int tw_i = m_tile % p.tiles_w;
+      m_tile /= p.tiles_w;
+      const int th_i = m_tile % p.tiles_h;
+      const int img = m_tile / p.tiles_h;
+      const int w = (tw_i << p.tw_log2) + wl, h = th_i * p.th + hl, n0 = n_tile * BN;
+      const bool valid = (w < p.Wo) && (h < p.Ho);
+      const int64_t off = (((int64_t)img * p.Ho + h) * p.Wo + w) * p.Cout + n0;
+      mbar_wait(&tfull_bar[acc], acc_phase, 400 + (int)acc);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c, r);
+        uint4 res[4];
+        const bool has_res = (p.residual != nullptr) && valid;
+        if (has_res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) res[i] = __ldg(rp + i);
+        }
+        float bv[32];
+        const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b4 = __ldg(bp + i);
+          bv[4 * i] = b4.x, bv[4 * i + 1] = b4.y, bv[4 * i + 2] = b4.z, bv[4 * i + 3] = b4.w;
+        }
+        tmem_ld_wait();
+        uint32_t o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float v0 = __uint_as_float(r[2 * i]) + bv[2 * i];
+          float v1 = __uint_as_float(r[2 * i + 1]) + bv[2 * i + 1];
+          if (has_res) {
+            const uint32_t rv = reinterpret_cast<const uint32_t*>(res)[i];
+            v0 += bf16lo(rv);
+            v1 += bf16hi(rv);
+          }
+          if (p.relu) {
+            v0 = fmaxf(v0, 0.f);
+            v1 = fmaxf(v1, 0.f);
+          }
+          o[i] = pack_bf16x2(v0, v1);
+        }
+        if (valid) {
+          uint4* op = reinterpret_cast<uint4*>(p.out + off + c);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) op[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1u;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+static int encode_act_map(CUtensorMap* m, const void* base, uint64_t C, uint64_t Wd, uint64_t Hd, uint64_t Nd,
+                          uint64_t strideW, uint64_t strideH, uint64_t strideN, uint32_t boxW, uint32_t boxH) {
+  encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return NBC_ERR_DEVICE;
+  }
+  cuuint64_t dims[4] = {C, Wd, Hd, Nd};
+  cuuint64_t strides[3] = {strideW, strideH, strideN};
+  cuuint32_t box[4] = {64, boxW, boxH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(activation) failed: %d (C=%llu W=%llu H=%llu N=%llu box=%ux%u)", (int)r,
+              (unsigned long long)C, (unsigned long long)Wd, (unsigned long long)Hd, (unsigned long long)Nd, boxW, boxH);
+    return NBC_ERR_CUDA;
+  }
+  return 0;
+}
+
+static int encode_weight_map(CUtensorMap* m, const void* base, uint64_t K, uint64_t Cout, uint32_t boxN) {
+  encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return NBC_ERR_DEVICE;
+  }
+  cuuint64_t dims[2] = {K, Cout};
+  cuuint64_t strides[1] = {K * 2};
+  cuuint32_t box[2] = {64, boxN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(weights) failed: %d (K=%llu Cout=%llu)", (int)r, (unsigned long long)K,
+              (unsigned long long)Cout);
+    return NBC_ERR_CUDA;
+  }
+  return 0;
+}
+
+bool conv_tc_supported(const ConvGeom& g) {
+  if (g.Cin % 64 != 0 || g.Cout % 64 != 0) return false;
+  if (g.kh * g.kw > 9) return false;
+  if (g.stride != 1 && g.stride != 2) return false;
+  if (g.Ho() < 1 || g.Wo() < 1) return false;
+  if (g.stride == 2 && (g.H < 2 || g.W < 2)) return false;
+  return true;
+}
+
+static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+struct ConvTcLaunch {
+  ConvTcParams p;
+  int block_n;
+  int grid;
+};
+
+static int build_launch(const ConvGeom& g, const void* x, const void* w, const float* bias, const void* residual,
+                        void* y, ConvTcLaunch* L) {
+  ConvTcParams& p = L->p;
+  memset(&p, 0, sizeof(p));
+  const int Ho = g.Ho(), Wo = g.Wo();
+  // 128-pixel rectangle: fewest tiles, widest on ties
+  int best_tw = 128, best_tiles = INT32_MAX;
+  for (int tw = 128; tw >= 8; tw >>= 1) {
+    const int th = 128 / tw;
+    const int tiles = ceil_div(Wo, tw) * ceil_div(Ho, th);
+    if (tiles < best_tiles) best_tiles = tiles, best_tw = tw;
+  }
+  p.tw = best_tw;
+  p.th = 128 / best_tw;
+  p.tw_log2 = 0;
+  while ((1 << p.tw_log2) < p.tw) ++p.tw_log2;
+  p.tiles_w = ceil_div(Wo, p.tw);
+  p.tiles_h = ceil_div(Ho, p.th);
+  p.N = g.N, p.Ho = Ho, p.Wo = Wo, p.Cout = g.Cout;
+  p.num_m_tiles = g.N * p.tiles_w * p.tiles_h;
+  const int bn = (g.Cout % 256 == 0) ? 256 : (g.Cout % 128 == 0 ? 128 : 64);
+  L->block_n = bn;
+  p.num_n_tiles = g.Cout / bn;
+  p.n_taps = g.kh * g.kw;
+  p.cblocks = g.Cin / 64;
+  p.relu = g.relu;
+  p.bias = bias;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.out = reinterpret_cast<__nv_bfloat16*>(y);
+
+  const uint64_t eb = 2;  // bytes per element
+  const char* xb = reinterpret_cast<const char*>(x);
+  if (g.stride == 1) {
+    int rc = encode_act_map(&p.tmA[0], xb, g.Cin, g.W, g.H, g.N, (uint64_t)g.Cin * eb, (uint64_t)g.W * g.Cin * eb,
+                            (uint64_t)g.H * g.W * g.Cin * eb, p.tw, p.th);
+    if (rc) return rc;
+    for (int ky = 0; ky < g.kh; ++ky)
+      for (int kx = 0; kx < g.kw; ++kx) {
+        const int t = ky * g.kw + kx;
+        p.tap_map[t] = 0;
+        p.tap_dh[t] = (int16_t)(ky * g.dil - g.pad);
+        p.tap_dw[t] = (int16_t)(kx * g.dil - g.pad);
+      }
+  } else {
+    bool used[4] = {false, false, false, false};
+    for (int ky = 0; ky < g.kh; ++ky)
+      for (int kx = 0; kx < g.kw; ++kx) {
+        const int t = ky * g.kw + kx;
+        const int oy = ky * g.dil - g.pad, ox = kx * g.dil - g.pad;
+        const int py = ((oy % 2) + 2) % 2, px = ((ox % 2) + 2) % 2;
+        p.tap_map[t] = (int8_t)(py * 2 + px);
+        p.tap_dh[t] = (int16_t)floordiv(oy, 2);
+        p.tap_dw[t] = (int16_t)floordiv(ox, 2);
+        used[py * 2 + px] = true;
+      }
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        if (!used[py * 2 + px]) continue;
+        const uint64_t Wd = (uint64_t)(g.W - px + 1) / 2, Hd = (uint64_t)(g.H - py + 1) / 2;
+        const char* base = xb + ((uint64_t)py * g.W + px) * g.Cin * eb;
+        int rc = encode_act_map(&p.tmA[py * 2 + px], base, g.Cin, Wd, Hd, g.N, 2ull * g.Cin * eb,
+                                2ull * g.W * g.Cin * eb, (uint64_t)g.H * g.W * g.Cin * eb, p.tw, p.th);
+        if (rc) return rc;
+      }
+    // the prefetch in the kernel touches tmA[0]; make sure it is a valid map
+    if (!used[0]) p.tmA[0] = p.tmA[p.tap_map[0]];
+  }
+  int rc = encode_weight_map(&p.tmB, w, (uint64_t)p.n_taps * g.Cin, g.Cout, bn);
+  if (rc) return rc;
+  const int total = p.num_m_tiles * p.num_n_tiles;
+  const int sms = sm_count();
+  L->grid = total < sms ? total : sms;
+  return 0;
+}
+
+template <int BN>
+static int launch_bn(const ConvTcLaunch& L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    NBC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::kSmemBytes));
+    attr_set = true;
+  }
+  conv_tc_kernel<BN><<<L.grid, kTcThreads, TcCfg<BN>::kSmemBytes, stream>>>(L.p);
+  NBC_CHECK_LAUNCH();
+  return 0;
+}
+
+int conv_tc_prepare(const ConvGeom& g, const void* x, const void* w, const float* bias, const void* residual, void* y,
+                    ConvTcPrepared* out) {
+  static_assert(sizeof(ConvTcLaunch) <= sizeof(out->storage), "ConvTcPrepared::storage too small");
+  if (!conv_tc_supported(g)) {
+    set_error("conv_tc: unsupported shape Cin=%d Cout=%d k=%dx%d stride=%d", g.Cin, g.Cout, g.kh, g.kw, g.stride);
+    return NBC_ERR_INVALID;
+  }
+  ConvTcLaunch* L = reinterpret_cast<ConvTcLaunch*>(out->storage);
+  return build_launch(g, x, w, bias, residual, y, L);
+}
+
+int conv_tc_run(const ConvTcPrepared* prep, cudaStream_t stream) {
+  const ConvTcLaunch* L = reinterpret_cast<const ConvTcLaunch*>(prep->storage);
+  switch (L->block_n) {
+    case 256: return launch_bn<256>(*L, stream);
+    case 128: return launch_bn<128>(*L, stream);
+    default: return launch_bn<64>(*L, stream);
+  }
+}
+
+int conv_tc(const ConvGeom& g, const void* x, const void* w, const float* bias, const void* residual, void* y,
+            cudaStream_t stream) {
+  ConvTcPrepared prep;
+  int rc = conv_tc_prepare(g, x, w, bias, residual, y, &prep);
+  if (rc) return rc;
+  return conv_tc_run(&prep, stream);
+}
+
+}  // namespace nbc

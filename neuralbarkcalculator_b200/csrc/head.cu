@@ -1,0 +1,161 @@
+// Head tail + K3.
+//  * nbc_head_1x1: Dropout (identity in eval) + Conv2d(512, 3, 1) with bias (models.py:113-124) on the bf16
+//    NHWC features, f32 weights, f32 planar logits [N,3,h*w].  HBM-bound: one warp per pixel, 32 B per lane.
+//  * nbc_upsample_argmax / nbc_upsample_bicubic: F.interpolate(mode='bicubic', align_corners=False)
+//    (models.py:38-41) fused with torch.argmax(dim=1) (models.py:270).  The 12.6 MB f32 full-resolution logits
+//    are never written in the argmax variant.  Index / weight arithmetic follows torch's upsample_bicubic2d in
+//    f32 with explicit IEEE operations (no fma contraction) in the order of oracle/model.py
+//    ``upsample_bicubic_restated`` so the result is bit-identical to that restatement.
+#include "common.cuh"
+
+namespace nbc {
+
+__global__ void __launch_bounds__(256) head1x1_kernel(const __nv_bfloat16* __restrict__ x, int64_t P, int N, int Cin,
+                                                      const float* __restrict__ w, const float* __restrict__ bias,
+                                                      float* __restrict__ logits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t M = (int64_t)N * P;
+  const float b0 = __ldg(bias), b1 = __ldg(bias + 1), b2 = __ldg(bias + 2);
+  for (int64_t m = warp_global; m < M; m += nwarps) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    const __nv_bfloat16* xr = x + m * Cin;
+    for (int c = lane * 8; c < Cin; c += 256) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(xr + c));
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float f0 = bf16lo(u[k]), f1 = bf16hi(u[k]);
+        const int ci = c + 2 * k;
+        a0 = fmaf(f0, __ldg(w + ci), a0), a0 = fmaf(f1, __ldg(w + ci + 1), a0);
+        a1 = fmaf(f0, __ldg(w + Cin + ci), a1), a1 = fmaf(f1, __ldg(w + Cin + ci + 1), a1);
+        a2 = fmaf(f0, __ldg(w + 2 * Cin + ci), a2), a2 = fmaf(f1, __ldg(w + 2 * Cin + ci + 1), a2);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) {
+      const int64_t img = m / P, pix = m - img * P;
+      float* o = logits + img * 3 * P + pix;
+      o[0] = a0 + b0;
+      o[P] = a1 + b1;
+      o[2 * P] = a2 + b2;
+    }
+  }
+}
+
+// torch cubic convolution coefficients, A = -0.75, evaluated with separately rounded f32 operations
+__device__ __forceinline__ float cc1(float x) {  // |x| <= 1 : ((A+2)x - (A+3)) x x + 1
+  const float a = __fsub_rn(__fmul_rn(1.25f, x), 2.25f);
+  return __fadd_rn(__fmul_rn(__fmul_rn(a, x), x), 1.f);
+}
+__device__ __forceinline__ float cc2(float x) {  // 1 < |x| < 2 : ((A x - 5A) x + 8A) x - 4A
+  const float a = __fsub_rn(__fmul_rn(-0.75f, x), -3.75f);
+  const float b = __fadd_rn(__fmul_rn(a, x), -6.f);
+  return __fsub_rn(__fmul_rn(b, x), -3.f);
+}
+__device__ __forceinline__ void cubic_taps(int dst, float scale, int in_size, int (&idx)[4], float (&wt)[4]) {
+  const float src = __fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f);
+  const float fl = floorf(src);
+  const float t = __fsub_rn(src, fl);
+  const int i0 = (int)fl;
+  const float omt = __fsub_rn(1.f, t);
+  wt[0] = cc2(__fadd_rn(t, 1.f));
+  wt[1] = cc1(t);
+  wt[2] = cc1(omt);
+  wt[3] = cc2(__fadd_rn(omt, 1.f));
+#pragma unroll
+  for (int k = 0; k < 4; ++k) idx[k] = min(max(i0 - 1 + k, 0), in_size - 1);
+}
+__device__ __forceinline__ float cubic_sample(const float* __restrict__ plane, int w, const int (&iy)[4],
+                                              const float (&wy)[4], const int (&ix)[4], const float (&wx)[4]) {
+  float out = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float* r = plane + (int64_t)iy[i] * w;
+    float inner = __fmul_rn(__ldg(r + ix[0]), wx[0]);
+    inner = __fadd_rn(inner, __fmul_rn(__ldg(r + ix[1]), wx[1]));
+    inner = __fadd_rn(inner, __fmul_rn(__ldg(r + ix[2]), wx[2]));
+    inner = __fadd_rn(inner, __fmul_rn(__ldg(r + ix[3]), wx[3]));
+    const float term = __fmul_rn(inner, wy[i]);
+    out = (i == 0) ? term : __fadd_rn(out, term);
+  }
+  return out;
+}
+
+template <bool kArgmax>
+__global__ void __launch_bounds__(256) upsample_kernel(const float* __restrict__ logits, int N, int C, int h, int w,
+                                                       int H, int W, float scale_y, float scale_x,
+                                                       uint8_t* __restrict__ mask, float* __restrict__ out) {
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = blockIdx.y;
+  const int n = blockIdx.z;
+  if (X >= W) return;
+  int ix[4], iy[4];
+  float wx[4], wy[4];
+  cubic_taps(X, scale_x, w, ix, wx);
+  cubic_taps(Y, scale_y, h, iy, wy);
+  const int64_t plane = (int64_t)h * w;
+  if (kArgmax) {
+    float best = 0.f;
+    int arg = 0;
+    for (int c = 0; c < C; ++c) {
+      const float v = cubic_sample(logits + ((int64_t)n * C + c) * plane, w, iy, wy, ix, wx);
+      if (c == 0 || v > best) best = v, arg = c;  // ties -> lowest index (torch.argmax)
+    }
+    mask[((int64_t)n * H + Y) * W + X] = (uint8_t)arg;
+  } else {
+    for (int c = 0; c < C; ++c)
+      out[(((int64_t)n * C + c) * H + Y) * W + X] =
+          cubic_sample(logits + ((int64_t)n * C + c) * plane, w, iy, wy, ix, wx);
+  }
+}
+
+}  // namespace nbc
+
+using namespace nbc;
+
+extern "C" int nbc_head_1x1(const void* x_bf16, int64_t pixels_per_image, int N, int Cin, const float* w3xC,
+                            const float* bias3, float* logits_planar, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  NBC_REQUIRE(x_bf16 && w3xC && bias3 && logits_planar, "nbc_head_1x1: null pointer");
+  NBC_REQUIRE(Cin % 8 == 0 && N > 0 && pixels_per_image > 0, "nbc_head_1x1: bad shape");
+  const int64_t M = (int64_t)N * pixels_per_image;
+  const int64_t want = ceil_div64(M, 8);
+  const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+  head1x1_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x_bf16), pixels_per_image, N, Cin,
+                                             w3xC, bias3, logits_planar);
+  NBC_CHECK_LAUNCH();
+  return 0;
+}
+
+static int upsample_common(const float* logits, int N, int C, int h, int w, int H, int W, uint8_t* mask, float* out,
+                           cudaStream_t stream) {
+  NBC_REQUIRE(logits && (mask || out), "nbc_upsample: null pointer");
+  NBC_REQUIRE(N > 0 && C > 0 && h > 0 && w > 0 && H > 0 && W > 0 && H <= 65535 && N <= 65535, "nbc_upsample: bad shape");
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;  // IEEE f32 division, as torch
+  dim3 grid(ceil_div(W, 256), H, N);
+  if (mask)
+    upsample_kernel<true><<<grid, 256, 0, stream>>>(logits, N, C, h, w, H, W, sy, sx, mask, nullptr);
+  else
+    upsample_kernel<false><<<grid, 256, 0, stream>>>(logits, N, C, h, w, H, W, sy, sx, nullptr, out);
+  NBC_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int nbc_upsample_argmax(const float* logits, int N, int h, int w, int H, int W, uint8_t* mask,
+                                   void* stream) {
+  NBC_REQUIRE(mask, "nbc_upsample_argmax: null mask");
+  return upsample_common(logits, N, 3, h, w, H, W, mask, nullptr, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nbc_upsample_bicubic(const float* logits, int N, int C, int h, int w, int H, int W, float* out,
+                                    void* stream) {
+  NBC_REQUIRE(out, "nbc_upsample_bicubic: null out");
+  return upsample_common(logits, N, C, h, w, H, W, nullptr, out, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,183 @@
+// Stem of the network: ToTensor + Normalize (dataset.py:181-190, models.py:233-237) fused into
+// conv1 7x7/2 pad 3 + bn1 + ReLU (torchvision resnet50 stem, models.py:127-131), then maxpool 3x3/2 pad 1.
+//
+// The input is the u8 NHWC image as decoded from the processed PNG; normalisation is done in f32 *before* the
+// zero padding exactly as the reference does ((u8/255 - mean)/std, IEEE div/sub/div), so the border is right.
+// K = 7*7*3 = 147 is too ragged for a TMA/UMMA tile; this first version runs on CUDA cores in f32:
+// one CTA = 16x16 output pixels x 64 channels, input tile and all weights staged in shared memory.
+#include "common.cuh"
+
+namespace nbc {
+
+constexpr int ST_T = 16;                    // output tile edge
+constexpr int ST_IN = 2 * ST_T + 5;         // 37 input rows / cols
+constexpr int ST_W_FLOATS = 147 * 64;       // [tap*3+c][oc]
+constexpr int ST_IN_FLOATS = ST_IN * ST_IN * 3;
+constexpr int ST_SMEM = (ST_W_FLOATS + ST_IN_FLOATS) * 4;
+
+struct StemParams {
+  const uint8_t* img;   // u8 NHWC (kF32 == false)
+  const float* xf;      // f32 NCHW, already normalised (kF32 == true)
+  const float* w;     // [64][7][7][3], BN folded
+  const float* bias;  // [64]
+  __nv_bfloat16* out; // [N][Ho][Wo][64]
+  int N, H, W, Ho, Wo;
+  float mean[3], std[3];
+};
+
+template <bool kF32>
+__global__ void __launch_bounds__(256) stem_kernel(const StemParams p) {
+  extern __shared__ float smem_f[];
+  float* sw = smem_f;                 // [147][64]
+  float* sin = smem_f + ST_W_FLOATS;  // [37][37][3]
+  const int tid = threadIdx.x;
+  const int img = blockIdx.z;
+  const int oh0 = blockIdx.y * ST_T, ow0 = blockIdx.x * ST_T;
+  for (int i = tid; i < ST_W_FLOATS; i += 256) {
+    const int oc = i / 147, k = i - oc * 147;  // source order [oc][k]
+    sw[k * 64 + oc] = __ldg(p.w + i);
+  }
+  const int ih0 = 2 * oh0 - 3, iw0 = 2 * ow0 - 3;
+  for (int i = tid; i < ST_IN * ST_IN; i += 256) {
+    const int r = i / ST_IN, c = i - r * ST_IN;
+    const int ih = ih0 + r, iw = iw0 + c;
+    float v[3] = {0.f, 0.f, 0.f};
+    if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
+      if (kF32) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) v[ch] = __ldg(p.xf + (((int64_t)img * 3 + ch) * p.H + ih) * p.W + iw);
+      } else {
+        const uint8_t* s = p.img + (((int64_t)img * p.H + ih) * p.W + iw) * 3;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+          v[ch] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)s[ch], 255.f), p.mean[ch]), p.std[ch]);
+      }
+    }
+    sin[i * 3] = v[0], sin[i * 3 + 1] = v[1], sin[i * 3 + 2] = v[2];
+  }
+  __syncthreads();
+
+  const int px = tid & 15, py = tid >> 4;
+  float acc[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+  for (int ky = 0; ky < 7; ++ky) {
+    const float* row = sin + ((2 * py + ky) * ST_IN + 2 * px) * 3;
+    const float* wk = sw + ky * 21 * 64;
+#pragma unroll 3
+    for (int j = 0; j < 21; ++j) {  // kx*3 + c
+      const float v = row[j];
+      const float4* w4 = reinterpret_cast<const float4*>(wk + j * 64);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const float4 w = w4[q];
+        acc[4 * q] = fmaf(v, w.x, acc[4 * q]);
+        acc[4 * q + 1] = fmaf(v, w.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(v, w.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(v, w.w, acc[4 * q + 3]);
+      }
+    }
+  }
+  const int oh = oh0 + py, ow = ow0 + px;
+  if (oh < p.Ho && ow < p.Wo) {
+    uint4* o = reinterpret_cast<uint4*>(p.out + (((int64_t)img * p.Ho + oh) * p.Wo + ow) * 64);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint32_t r[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = q * 8 + 2 * k;
+        r[k] = pack_bf16x2(fmaxf(acc[c] + __ldg(p.bias + c), 0.f), fmaxf(acc[c + 1] + __ldg(p.bias + c + 1), 0.f));
+      }
+      o[q] = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+  }
+}
+
+// maxpool 3x3 stride 2 pad 1 (padding = -inf), bf16 NHWC, 8 channels per thread
+__global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C,
+                                                      int Ho, int Wo, __nv_bfloat16* __restrict__ y) {
+  const int cg = C >> 3;
+  const int64_t total = (int64_t)N * Ho * Wo * cg;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cg);
+    int64_t t = i / cg;
+    const int wo = (int)(t % Wo);
+    t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    __nv_bfloat162 m[4];
+    const __nv_bfloat162 ninf = __floats2bfloat162_rn(-INFINITY, -INFINITY);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m[k] = ninf;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int h = 2 * ho + dy;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int w = 2 * wo + dx;
+        if (w < 0 || w >= W) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)n * H + h) * W + w) * C + c8 * 8));
+        const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m[k] = __hmax2(m[k], v2[k]);
+      }
+    }
+    *reinterpret_cast<uint4*>(y + (((int64_t)n * Ho + ho) * Wo + wo) * C + c8 * 8) = *reinterpret_cast<uint4*>(m);
+  }
+}
+
+}  // namespace nbc
+
+using namespace nbc;
+
+static int stem_launch(const uint8_t* img, const float* xf, int N, int H, int W, const float* mean3, const float* std3,
+                       const float* w_stem, const float* bias, void* out, cudaStream_t stream) {
+  NBC_REQUIRE((img || xf) && w_stem && bias && out, "nbc_stem: null pointer");
+  NBC_REQUIRE(N > 0 && H > 0 && W > 0 && N <= 65535, "nbc_stem: bad shape");
+  static bool attr_set = false;
+  if (!attr_set) {
+    NBC_CUDA(cudaFuncSetAttribute(stem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+    NBC_CUDA(cudaFuncSetAttribute(stem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+    attr_set = true;
+  }
+  StemParams p;
+  p.img = img, p.xf = xf, p.w = w_stem, p.bias = bias, p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.N = N, p.H = H, p.W = W, p.Ho = (H + 6 - 7) / 2 + 1, p.Wo = (W + 6 - 7) / 2 + 1;
+  for (int i = 0; i < 3; ++i) p.mean[i] = mean3 ? mean3[i] : 0.f, p.std[i] = std3 ? std3[i] : 1.f;
+  dim3 grid(ceil_div(p.Wo, ST_T), ceil_div(p.Ho, ST_T), N);
+  if (xf)
+    stem_kernel<true><<<grid, 256, ST_SMEM, stream>>>(p);
+  else
+    stem_kernel<false><<<grid, 256, ST_SMEM, stream>>>(p);
+  NBC_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int nbc_stem_u8(const uint8_t* img, int N, int H, int W, const float* mean3_host, const float* std3_host,
+                           const float* w_stem, const float* bias, void* out, void* stream) {
+  NBC_REQUIRE(img && mean3_host && std3_host, "nbc_stem_u8: null pointer");
+  return stem_launch(img, nullptr, N, H, W, mean3_host, std3_host, w_stem, bias, out,
+                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nbc_stem_f32(const float* x_nchw, int N, int H, int W, const float* w_stem, const float* bias, void* out,
+                            void* stream) {
+  NBC_REQUIRE(x_nchw, "nbc_stem_f32: null pointer");
+  return stem_launch(nullptr, x_nchw, N, H, W, nullptr, nullptr, w_stem, bias, out,
+                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nbc_maxpool3x3s2_bf16(const void* x, int N, int H, int W, int C, void* y, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  NBC_REQUIRE(x && y, "nbc_maxpool3x3s2_bf16: null pointer");
+  NBC_REQUIRE(C % 8 == 0 && N > 0 && H > 0 && W > 0, "nbc_maxpool3x3s2_bf16: bad shape");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
+  const int blocks = (int)(ceil_div64(total, 256) < 148 * 16 ? ceil_div64(total, 256) : 148 * 16);
+  maxpool_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, Ho, Wo,
+                                             reinterpret_cast<__nv_bfloat16*>(y));
+  NBC_CHECK_LAUNCH();
+  return 0;
+}

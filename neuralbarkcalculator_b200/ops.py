@@ -1,0 +1,309 @@
+"""Tensor-level wrappers over the C-ABI (include/nbc.h).  torch is used for device memory and streams only:
+every function checks that its tensors are CUDA tensors on a B200 and raises otherwise -- no CPU fallback."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _stream(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _dev(t, name='tensor'):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError('%s must be a CUDA tensor: neuralbarkcalculator_b200 has no CPU path' % name)
+    _lib.require_device(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    return t
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _contig(t, dtype, name):
+    _dev(t, name)
+    if t.dtype != dtype:
+        raise RuntimeError('%s must be %s (got %s)' % (name, dtype, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ---- K1 -------------------------------------------------------------------------------------------------------
+def preprocess_4x(raw, H, W, pitch=None, bgr=False, bottom_up=False, workspace=None):
+    """raw: u8 CUDA tensor holding an H x W x 3 pixel array (row pitch ``pitch`` bytes).
+    Returns (out u8 [(H/4)*(W/4)*3] flat buffer, first_last int32[2] CUDA tensor).
+    The trimmed image is ``out[:(last-first)*(W/4)*3].view(last-first, W/4, 3)``.  (models.py:191-203)"""
+    lib = _lib.load()
+    raw = _contig(raw, torch.uint8, 'raw')
+    pitch = W * 3 if pitch is None else pitch
+    with torch.cuda.device(raw.device):
+        need = lib.nbc_preprocess_workspace_bytes(H, W)
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty(need, dtype=torch.uint8, device=raw.device)
+        out = torch.empty((H // 4) * (W // 4) * 3, dtype=torch.uint8, device=raw.device)
+        fl = torch.empty(2, dtype=torch.int32, device=raw.device)
+        _lib.check(lib.nbc_preprocess_4x_u8(_ptr(raw), H, W, pitch, (1 if bgr else 0) | (2 if bottom_up else 0), _ptr(out),
+                                            _ptr(fl), _ptr(workspace), workspace.numel(), _stream(raw.device)),
+                   'nbc_preprocess_4x_u8')
+    return out, fl
+
+
+def trim_u8(img):
+    """img: u8 CUDA [H, W, 3] that needs no resize -> (out flat, first_last).  (models.py:157-166, 200-201)"""
+    lib = _lib.load()
+    img = _contig(img, torch.uint8, 'img')
+    H, W = img.shape[0], img.shape[1]
+    with torch.cuda.device(img.device):
+        ws = torch.empty(lib.nbc_preprocess_workspace_bytes(max(H, 4) * 4, 4), dtype=torch.uint8, device=img.device)
+        out = torch.empty(H * W * 3, dtype=torch.uint8, device=img.device)
+        fl = torch.empty(2, dtype=torch.int32, device=img.device)
+        _lib.check(lib.nbc_trim_u8(_ptr(img), H, W, _ptr(out), _ptr(fl), _ptr(ws), ws.numel(), _stream(img.device)),
+                   'nbc_trim_u8')
+    return out, fl
+
+
+# ---- weights / single layers (unit-test surface) --------------------------------------------------------------------
+def fold_bn_pack(weight, bn=None, conv_bias=None, eps=1e-5, cin_pad=None):
+    """weight f32 OIHW (+ optional (gamma, beta, mean, var)) -> (bf16 [Cout,kh,kw,cin_pad], f32 bias[Cout])."""
+    lib = _lib.load()
+    weight = _contig(weight, torch.float32, 'weight')
+    Cout, Cin, kh, kw = weight.shape
+    cin_pad = Cin if cin_pad is None else cin_pad
+    g = b = m = v = None
+    if bn is not None:
+        g, b, m, v = [_contig(t, torch.float32, 'bn') for t in bn]
+    cb = _contig(conv_bias, torch.float32, 'conv_bias') if conv_bias is not None else None
+    with torch.cuda.device(weight.device):
+        wp = torch.empty((Cout, kh, kw, cin_pad), dtype=torch.bfloat16, device=weight.device)
+        bias = torch.empty(Cout, dtype=torch.float32, device=weight.device)
+        _lib.check(lib.nbc_fold_bn_pack(_ptr(weight), _ptr(g), _ptr(b), _ptr(m), _ptr(v), _ptr(cb), eps, Cout, Cin, kh, kw,
+                                        cin_pad, _ptr(wp), _ptr(bias), _stream(weight.device)), 'nbc_fold_bn_pack')
+    return wp, bias
+
+
+def conv_bf16(x, w_packed, bias, stride=1, pad=0, dil=1, relu=False, residual=None, impl=0):
+    """x bf16 NHWC [N,H,W,Cin]; w_packed bf16 [Cout,kh,kw,Cin]; -> bf16 NHWC [N,Ho,Wo,Cout]."""
+    lib = _lib.load()
+    x = _contig(x, torch.bfloat16, 'x')
+    w_packed = _contig(w_packed, torch.bfloat16, 'w_packed')
+    bias = _contig(bias, torch.float32, 'bias')
+    N, H, W, Cin = x.shape
+    Cout, kh, kw, cin2 = w_packed.shape
+    if cin2 != Cin:
+        raise RuntimeError('conv_bf16: channel mismatch %d vs %d' % (Cin, cin2))
+    Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
+    if residual is not None:
+        residual = _contig(residual, torch.bfloat16, 'residual')
+        if tuple(residual.shape) != (N, Ho, Wo, Cout):
+            raise RuntimeError('conv_bf16: residual shape mismatch')
+    with torch.cuda.device(x.device):
+        y = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
+        d = _lib.ConvDesc(N, H, W, Cin, Cout, kh, kw, stride, pad, dil, 1 if relu else 0, impl)
+        _lib.check(lib.nbc_conv_bf16(C.byref(d), _ptr(x), _ptr(w_packed), _ptr(bias), _ptr(residual), _ptr(y),
+                                     _stream(x.device)), 'nbc_conv_bf16')
+    return y
+
+
+def stem_u8(img, mean, std, w_stem, bias):
+    lib = _lib.load()
+    img = _contig(img, torch.uint8, 'img')
+    N, H, W, _ = img.shape
+    m3 = (C.c_float * 3)(*mean)
+    s3 = (C.c_float * 3)(*std)
+    with torch.cuda.device(img.device):
+        out = torch.empty((N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64), dtype=torch.bfloat16, device=img.device)
+        _lib.check(lib.nbc_stem_u8(_ptr(img), N, H, W, m3, s3, _ptr(_contig(w_stem, torch.float32, 'w_stem')),
+                                   _ptr(_contig(bias, torch.float32, 'bias')), _ptr(out), _stream(img.device)), 'nbc_stem_u8')
+    return out
+
+
+def stem_f32(x, w_stem, bias):
+    lib = _lib.load()
+    x = _contig(x, torch.float32, 'x')
+    N, _, H, W = x.shape
+    with torch.cuda.device(x.device):
+        out = torch.empty((N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64), dtype=torch.bfloat16, device=x.device)
+        _lib.check(lib.nbc_stem_f32(_ptr(x), N, H, W, _ptr(_contig(w_stem, torch.float32, 'w_stem')),
+                                    _ptr(_contig(bias, torch.float32, 'bias')), _ptr(out), _stream(x.device)), 'nbc_stem_f32')
+    return out
+
+
+def maxpool3x3s2(x):
+    lib = _lib.load()
+    x = _contig(x, torch.bfloat16, 'x')
+    N, H, W, Cc = x.shape
+    with torch.cuda.device(x.device):
+        y = torch.empty((N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, Cc), dtype=torch.bfloat16, device=x.device)
+        _lib.check(lib.nbc_maxpool3x3s2_bf16(_ptr(x), N, H, W, Cc, _ptr(y), _stream(x.device)), 'nbc_maxpool3x3s2_bf16')
+    return y
+
+
+def head_1x1(x, weight, bias):
+    """x bf16 NHWC [N,h,w,Cin], weight f32 [3,Cin], bias f32[3] -> f32 [N,3,h,w]."""
+    lib = _lib.load()
+    x = _contig(x, torch.bfloat16, 'x')
+    N, h, w, Cin = x.shape
+    with torch.cuda.device(x.device):
+        out = torch.empty((N, 3, h, w), dtype=torch.float32, device=x.device)
+        _lib.check(lib.nbc_head_1x1(_ptr(x), h * w, N, Cin, _ptr(_contig(weight, torch.float32, 'weight')),
+                                    _ptr(_contig(bias, torch.float32, 'bias')), _ptr(out), _stream(x.device)), 'nbc_head_1x1')
+    return out
+
+
+# ---- K3 -------------------------------------------------------------------------------------------------------
+def upsample_argmax(logits, size, out=None):
+    """logits f32 [N,3,h,w] -> u8 mask [N,H,W] = argmax(bicubic upsample)  (models.py:38-41, 270)."""
+    lib = _lib.load()
+    logits = _contig(logits, torch.float32, 'logits')
+    N, Cc, h, w = logits.shape
+    if Cc != 3:
+        raise RuntimeError('upsample_argmax expects 3 classes')
+    H, W = size
+    with torch.cuda.device(logits.device):
+        if out is None:
+            out = torch.empty((N, H, W), dtype=torch.uint8, device=logits.device)
+        _lib.check(lib.nbc_upsample_argmax(_ptr(logits), N, h, w, H, W, _ptr(out), _stream(logits.device)),
+                   'nbc_upsample_argmax')
+    return out
+
+
+def upsample_bicubic(logits, size):
+    lib = _lib.load()
+    logits = _contig(logits, torch.float32, 'logits')
+    N, Cc, h, w = logits.shape
+    H, W = size
+    with torch.cuda.device(logits.device):
+        out = torch.empty((N, Cc, H, W), dtype=torch.float32, device=logits.device)
+        _lib.check(lib.nbc_upsample_bicubic(_ptr(logits), N, Cc, h, w, H, W, _ptr(out), _stream(logits.device)),
+                   'nbc_upsample_bicubic')
+    return out
+
+
+# ---- K5 -------------------------------------------------------------------------------------------------------
+def remove_small_zones_u8(mask, threshold=150, exclude_nodes=False, workspace=None):
+    """mask u8 CUDA [N,H,W], modified in place.  Returns (mask, counts int32 [N,3]).  (utils.py:135-148)"""
+    lib = _lib.load()
+    _dev(mask, 'mask')
+    if mask.dtype != torch.uint8 or not mask.is_contiguous() or mask.dim() != 3:
+        raise RuntimeError('remove_small_zones_u8 expects a contiguous u8 [N,H,W] tensor')
+    N, H, W = mask.shape
+    with torch.cuda.device(mask.device):
+        need = lib.nbc_ccl_workspace_bytes(N, H, W)
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty(need, dtype=torch.uint8, device=mask.device)
+        counts = torch.empty((N, 3), dtype=torch.int32, device=mask.device)
+        _lib.check(lib.nbc_remove_small_zones(_ptr(mask), N, H, W, int(threshold), 1 if exclude_nodes else 0, _ptr(counts),
+                                              _ptr(workspace), workspace.numel(), _stream(mask.device)),
+                   'nbc_remove_small_zones')
+    return mask, counts
+
+
+# ---- K4 -------------------------------------------------------------------------------------------------------
+def wce_fwd_bwd(logits, target, weights, need_grad=True):
+    """logits f32 [N,3,H,W], target u8 or int64 [N,H,W], weights f32[3] -> (loss 0-dim f32, grad or None)."""
+    lib = _lib.load()
+    logits = _contig(logits, torch.float32, 'logits')
+    _dev(target, 'target')
+    if target.dtype not in (torch.uint8, torch.int64):
+        raise RuntimeError('target must be uint8 or int64')
+    target = target.contiguous()
+    weights = _contig(weights, torch.float32, 'weights')
+    N, Cc, H, W = logits.shape
+    if Cc != 3 or tuple(target.shape) != (N, H, W):
+        raise RuntimeError('wce: expected logits [N,3,H,W] and target [N,H,W]')
+    with torch.cuda.device(logits.device):
+        ws = torch.empty(lib.nbc_wce_workspace_bytes(N, H, W), dtype=torch.uint8, device=logits.device)
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        grad = torch.empty_like(logits) if need_grad else None
+        _lib.check(lib.nbc_wce_fwd_bwd(_ptr(logits), _ptr(target), 1 if target.dtype == torch.int64 else 0, _ptr(weights), N,
+                                       H, W, _ptr(loss), _ptr(grad), _ptr(ws), ws.numel(), _stream(logits.device)),
+                   'nbc_wce_fwd_bwd')
+    return loss, grad
+
+
+# ---- the network plan ---------------------------------------------------------------------------------------------
+class Plan:
+    """Owns an nbc_plan (BN-folded bf16 weights on the device) built from the 326 state_dict tensors."""
+
+    def __init__(self, tensors, mean, std, device):
+        lib = _lib.load()
+        self.device = torch.device(device)
+        _lib.require_device(self.device.index if self.device.index is not None else torch.cuda.current_device())
+        keep = []
+        for t in tensors:
+            _dev(t, 'state_dict tensor')
+            keep.append(t.detach().contiguous() if t.dtype != torch.int64 else t.detach())
+        arr = (C.c_void_p * len(keep))(*[t.data_ptr() for t in keep])
+        m3 = (C.c_float * 3)(*mean)
+        s3 = (C.c_float * 3)(*std)
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream().synchronize()
+            self.handle = lib.nbc_plan_create(arr, len(keep), m3, s3)
+        if not self.handle:
+            raise RuntimeError('nbc_plan_create failed: ' + _lib.last_error())
+        self._ws = None
+        self._lib = lib
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                self._lib.nbc_plan_destroy(C.c_void_p(self.handle))
+                self.handle = None
+        except Exception:
+            pass
+
+    def set_impl(self, impl):
+        _lib.check(self._lib.nbc_plan_set_impl(C.c_void_p(self.handle), int(impl)), 'nbc_plan_set_impl')
+
+    def _workspace(self, N, H, W):
+        need = self._lib.nbc_plan_workspace_bytes(C.c_void_p(self.handle), N, H, W) + 1024
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        off = (-self._ws.data_ptr()) % 1024
+        return self._ws.data_ptr() + off, self._ws.numel() - off
+
+    def forward(self, inp, out=None):
+        """inp: u8 NHWC [N,H,W,3] (normalised inside) or f32 NCHW [N,3,H,W] (already normalised).
+        Returns f32 low-resolution logits [N,3,h,w]."""
+        _dev(inp, 'input')
+        if inp.dtype == torch.uint8:
+            inp = inp if inp.is_contiguous() else inp.contiguous()
+            N, H, W, c = inp.shape
+            kind = 0
+        elif inp.dtype == torch.float32:
+            inp = inp if inp.is_contiguous() else inp.contiguous()
+            N, c, H, W = inp.shape
+            kind = 1
+        else:
+            raise RuntimeError('Plan.forward expects u8 NHWC or f32 NCHW input')
+        if c != 3:
+            raise RuntimeError('Plan.forward expects 3 channels')
+        h = ((((H - 1) // 2 + 1) - 1) // 2 + 1 - 1) // 2 + 1
+        w = ((((W - 1) // 2 + 1) - 1) // 2 + 1 - 1) // 2 + 1
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty((N, 3, h, w), dtype=torch.float32, device=self.device)
+            ws_ptr, ws_bytes = self._workspace(N, H, W)
+            _lib.check(self._lib.nbc_plan_forward(C.c_void_p(self.handle), _ptr(inp), kind, N, H, W, _ptr(out),
+                                                  C.c_void_p(ws_ptr), ws_bytes, _stream(self.device)), 'nbc_plan_forward')
+        return out
+
+    def profile(self, inp):
+        """Per-layer CUDA-event timing of one forward: list of (ms, flops)."""
+        _dev(inp, 'input')
+        N, H, W, _ = inp.shape
+        h = ((((H - 1) // 2 + 1) - 1) // 2 + 1 - 1) // 2 + 1
+        w = ((((W - 1) // 2 + 1) - 1) // 2 + 1 - 1) // 2 + 1
+        with torch.cuda.device(self.device):
+            out = torch.empty((N, 3, h, w), dtype=torch.float32, device=self.device)
+            ws_ptr, ws_bytes = self._workspace(N, H, W)
+            ms = (C.c_float * 128)()
+            fl = (C.c_double * 128)()
+            n = self._lib.nbc_plan_profile(C.c_void_p(self.handle), _ptr(inp), 0, N, H, W, _ptr(out), C.c_void_p(ws_ptr),
+                                           ws_bytes, _stream(self.device), ms, fl, 128)
+            if n < 0:
+                _lib.check(n, 'nbc_plan_profile')
+        return [(ms[i], fl[i]) for i in range(n)]

@@ -146,6 +146,37 @@ def bicubic_weights_f32(in_size, out_size):
         return ((A * x - np.float32(5) * A) * x + np.float32(8) * A) * x - np.float32(4) * A
 
     one = np.float32(1)
-    w = np.stack([c2(t + one), c1(t), c1(one - t), c2(np.float32(2) - t)], axis=1).astype(np.float32)
+    w = np.stack([c2(t + one), c1(t), c1(one - t), c2((one - t) + one)], axis=1).astype(np.float32)
     idx = np.clip(i0[:, None] + np.arange(-1, 3)[None, :], 0, in_size - 1)
     return idx, w
+
+
+def upsample_bicubic_restated(low, size):
+    """Bit-exact specification of the CUDA upsample kernel (head.cu): torch's bicubic arithmetic restated in float32
+    with one rounding per operation (no fma) and a fixed summation order:
+
+        inner_i = ((v[i,0]*wx0 + v[i,1]*wx1) + v[i,2]*wx2) + v[i,3]*wx3      (x taps, per source row i)
+        out     = ((inner_0*wy0 + inner_1*wy1) + inner_2*wy2) + inner_3*wy3
+
+    low: f32 array [N,C,h,w] -> f32 [N,C,H,W].  torch's own kernel differs from this by float round-off only
+    (<= ~2e-6 relative; checked in tests/test_oracle.py)."""
+    low = np.asarray(low, dtype=np.float32)
+    N, C, h, w = low.shape
+    H, W = size
+    iy, wy = bicubic_weights_f32(h, H)
+    ix, wx = bicubic_weights_f32(w, W)
+    out = None
+    for i in range(4):
+        rows = low[:, :, iy[:, i], :]                      # [N,C,H,w]
+        inner = None
+        for j in range(4):
+            term = (rows[:, :, :, ix[:, j]] * wx[None, None, None, :, j]).astype(np.float32)
+            inner = term if inner is None else (inner + term).astype(np.float32)
+        t = (inner * wy[None, None, :, i, None]).astype(np.float32)
+        out = t if out is None else (out + t).astype(np.float32)
+    return out
+
+
+def argmax_lowest(up):
+    """torch.argmax(dim=1) semantics: first (lowest) index among ties."""
+    return np.argmax(np.asarray(up), axis=1).astype(np.uint8)

@@ -1,0 +1,312 @@
+"""GPU parity tests (run on a B200: ``pytest -m gpu``).  Every test calls the CUDA path through the C-ABI
+(neuralbarkcalculator_b200.ops -> libnbc.so) and compares with the CPU oracle / golden fixtures.
+
+Bars: bit-exact for byte / integer / index work (resize+trim, region removal, class counts, argmax given logits);
+floating point within the tolerance written in each test."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import losses as olosses
+from oracle import model as omodel
+from oracle import postprocess as opost
+from oracle import preprocess as opre
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+IMPLS = [int(v) for v in os.environ.get('NBC_TEST_IMPLS', '2,1').split(',')]   # 1 = tcgen05, 2 = mma.sync
+
+
+def _ops():
+    from neuralbarkcalculator_b200 import ops
+    return ops
+
+
+# ------------------------------------------------------------------------------------------------- K1 preprocess
+def _run_pre(raw_np, dev, bgr=False, bottom_up=False):
+    ops = _ops()
+    H, W, _ = raw_np.shape
+    src = raw_np
+    if bgr:
+        src = src[:, :, ::-1]
+    if bottom_up:
+        src = src[::-1]
+    t = torch.from_numpy(np.ascontiguousarray(src)).to(dev)
+    out, fl = ops.preprocess_4x(t.view(-1), H, W, bgr=bgr, bottom_up=bottom_up)
+    first, last = fl.tolist()
+    return out[:(last - first) * (W // 4) * 3].view(last - first, W // 4, 3).cpu().numpy(), first, last
+
+
+@pytest.mark.parametrize('bgr,bottom_up', [(False, False), (True, True), (True, False)])
+def test_preprocess_golden(cuda_device, golden_dir, bgr, bottom_up):
+    g = np.load(os.path.join(golden_dir, 'preprocess_small.npz'))
+    out, first, last = _run_pre(g['raw'], cuda_device, bgr, bottom_up)
+    assert (first, last) == (int(g['first']), int(g['last']))
+    assert np.array_equal(out, g['out'])
+
+
+def test_preprocess_full_size_and_edges(cuda_device):
+    raw, _, _ = synth.raw_image_u8(seed=3, size=4096, top=801, bottom=1199)
+    exp, f, l = opre.preprocess_u8(raw)
+    out, first, last = _run_pre(raw, cuda_device, bgr=True, bottom_up=True)
+    assert (first, last) == (f, l) and np.array_equal(out, exp)
+    # all dark -> nothing kept -> whole image (argmax of all-False is 0)
+    z = np.zeros((256, 256, 3), np.uint8)
+    out, first, last = _run_pre(z, cuda_device)
+    assert (first, last) == (0, 64) and not out.any()
+    # min >= 1 -> every pixel non-dark; max < 255 and min > 0 -> the clip to [min, max] is exercised
+    t = synth.texture_u8(256, 256, 9)
+    t = np.clip(t, 40, 200).astype(np.uint8)
+    t[::7, ::5] = 40
+    t[3::7, 2::5] = 200
+    big = np.ascontiguousarray(np.tile(t, (4, 4, 1))[:1024, :1024])     # 1024 -> 256
+    S = opre.resize4x_S(big)
+    Sc = np.clip(S, 256 * int(big.min()), 256 * int(big.max()))
+    expect = ((Sc + 128) >> 8).astype(np.uint8)
+    assert (S < 256 * int(big.min())).any() or (S > 256 * int(big.max())).any()     # clipping really happens
+    out, first, last = _run_pre(big, cuda_device)
+    assert (first, last) == (0, 256) and np.array_equal(out, expect)
+    # non-square (no trim) and a width that is not a multiple of 16 (unaligned path)
+    r = synth.texture_u8(64, 40, 2)
+    r[:16] = 0
+    out, first, last = _run_pre(r, cuda_device)
+    S = opre.resize4x_S(r)
+    expect = ((np.clip(S, 256 * int(r.min()), 256 * int(r.max())) + 128) >> 8).astype(np.uint8)
+    assert (first, last) == (0, 16) and np.array_equal(out, expect)
+
+
+def test_trim_u8(cuda_device):
+    ops = _ops()
+    img = synth.texture_u8(96, 96, 4)
+    img[:7] = 0
+    img[90:] = 0
+    img[30, :10] = 0
+    exp, f, l = opre.preprocess_u8(img)
+    out, fl = ops.trim_u8(torch.from_numpy(img).to(cuda_device))
+    first, last = fl.tolist()
+    assert (first, last) == (f, l)
+    assert np.array_equal(out[:(last - first) * 96 * 3].view(-1, 96, 3).cpu().numpy(), exp)
+
+
+# ------------------------------------------------------------------------------------------------- K2 convolutions
+# (Cin, Cout, k, stride, dil): the 24 tensor-core conv configurations of FCN-ResNet50
+CONV_SHAPES = [(64, 64, 1, 1, 1), (64, 64, 3, 1, 1), (64, 256, 1, 1, 1), (256, 64, 1, 1, 1), (256, 128, 1, 1, 1),
+               (128, 128, 3, 2, 1), (128, 128, 3, 1, 1), (128, 512, 1, 1, 1), (256, 512, 1, 2, 1), (512, 128, 1, 1, 1),
+               (512, 256, 1, 1, 1), (256, 256, 3, 1, 1), (256, 256, 3, 1, 2), (256, 1024, 1, 1, 1), (512, 1024, 1, 1, 1),
+               (1024, 256, 1, 1, 1), (1024, 512, 1, 1, 1), (512, 512, 3, 1, 2), (512, 512, 3, 1, 4), (512, 2048, 1, 1, 1),
+               (1024, 2048, 1, 1, 1), (2048, 512, 1, 1, 1), (2048, 512, 3, 1, 1)]
+
+
+def _conv_case(dev, Cin, Cout, k, stride, dil, N, H, W, relu, use_res, impl, seed=0):
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, H, W, Cin, generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / np.sqrt(Cin * k * k)).to(torch.float32)
+    gamma = torch.rand(Cout, generator=g) + 0.5
+    beta = torch.randn(Cout, generator=g) * 0.1
+    mean = torch.randn(Cout, generator=g) * 0.1
+    var = torch.rand(Cout, generator=g) + 0.5
+    pad = dil if k == 3 else 0
+    wp, bias = ops.fold_bn_pack(w.to(dev), (gamma.to(dev), beta.to(dev), mean.to(dev), var.to(dev)))
+    Ho = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    res = torch.randn(N, Ho, Wo, Cout, generator=g).to(torch.bfloat16) if use_res else None
+    y = ops.conv_bf16(x.to(dev), wp, bias, stride=stride, pad=pad, dil=dil, relu=relu,
+                      residual=res.to(dev) if use_res else None, impl=impl)
+    torch.cuda.synchronize()
+    # oracle: the same bf16-rounded operands in f32 on the CPU
+    wq = wp.float().cpu().permute(0, 3, 1, 2).contiguous()
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wq, bias.cpu(), stride=stride, padding=pad, dilation=dil)
+    if use_res:
+        ref = ref + res.float().permute(0, 3, 1, 2)
+    if relu:
+        ref = ref.relu()
+    ref = ref.permute(0, 2, 3, 1)
+    got = y.float().cpu()
+    assert got.shape == ref.shape
+    err = (got - ref).abs()
+    tol = 2.0 ** -7 * ref.abs() + 2e-2      # bf16 output rounding (2^-8 rel) + f32 accumulation-order slack
+    bad = (err > tol)
+    assert not bad.any(), 'max err %.4g at %s (ref %.4g) bad=%d' % (err.max(), np.unravel_index(err.argmax(), err.shape),
+                                                                   ref.flatten()[err.argmax()], int(bad.sum()))
+    # fold check: BN scale really went into the weights
+    scale = gamma / torch.sqrt(var + 1e-5)
+    assert torch.allclose(bias.cpu(), beta - mean * scale, atol=1e-6)
+    return float(err.max())
+
+
+@pytest.mark.parametrize('impl', IMPLS)
+@pytest.mark.parametrize('shape', CONV_SHAPES)
+def test_conv_all_shapes(cuda_device, shape, impl):
+    Cin, Cout, k, stride, dil = shape
+    # ragged spatial size (not a multiple of any tile), batch 2
+    _conv_case(cuda_device, Cin, Cout, k, stride, dil, N=2, H=27, W=40, relu=True, use_res=(k == 1 and Cout >= 256), impl=impl)
+
+
+@pytest.mark.parametrize('impl', IMPLS)
+def test_conv_full_width_rows(cuda_device, impl):
+    # the production geometry: 128-wide rows, trimmed height (77 rows), dilation 2 and 4
+    _conv_case(cuda_device, 256, 256, 3, 1, 2, N=1, H=77, W=128, relu=True, use_res=False, impl=impl, seed=1)
+    _conv_case(cuda_device, 512, 512, 3, 1, 4, N=1, H=16, W=128, relu=False, use_res=False, impl=impl, seed=2)
+    _conv_case(cuda_device, 128, 128, 3, 2, 1, N=1, H=33, W=255, relu=True, use_res=False, impl=impl, seed=3)
+    _conv_case(cuda_device, 256, 512, 1, 2, 1, N=2, H=31, W=256, relu=False, use_res=False, impl=impl, seed=4)
+
+
+def test_conv_tc_many_tiles(cuda_device):
+    # more tiles than SMs so the persistent loop, the smem ring wrap and both TMEM buffers are all exercised
+    _conv_case(cuda_device, 512, 1024, 1, 1, 1, N=3, H=64, W=128, relu=True, use_res=True, impl=1, seed=5)
+    _conv_case(cuda_device, 64, 64, 3, 1, 1, N=2, H=96, W=256, relu=True, use_res=False, impl=1, seed=6)
+
+
+# ------------------------------------------------------------------------------------------------- stem / pool / head
+def test_stem_maxpool_head(cuda_device):
+    ops = _ops()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(0)
+    img = synth.texture_u8(45, 70, 3)
+    w = torch.randn(64, 3, 7, 7, generator=g) * 0.1
+    bn = [torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.1, torch.randn(64, generator=g) * 0.1,
+          torch.rand(64, generator=g) + 0.5]
+    x = omodel.normalise_u8(img)
+    scale = bn[0] / torch.sqrt(bn[3] + 1e-5)
+    ref = torch.nn.functional.conv2d(x, w * scale.view(-1, 1, 1, 1), bn[1] - bn[2] * scale, stride=2, padding=3).relu()
+    # f32 fold of the stem weights happens inside nbc_plan_create; here emulate it with torch on the host
+    wf = (w * scale.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).contiguous().to(dev)
+    bf = (bn[1] - bn[2] * scale).to(dev)
+    y = ops.stem_u8(torch.from_numpy(img).unsqueeze(0).to(dev), omodel.DEFAULT_MEAN, omodel.DEFAULT_STD, wf, bf)
+    got = y.float().cpu().permute(0, 3, 1, 2)
+    assert (got - ref).abs().max() < 2.0 ** -8 * ref.abs().max() + 1e-3
+    y2 = ops.stem_f32(x.to(dev), wf, bf)
+    assert torch.equal(y2, y)
+    p = ops.maxpool3x3s2(y)
+    refp = torch.nn.functional.max_pool2d(y.float().cpu().permute(0, 3, 1, 2), 3, 2, 1)
+    assert torch.equal(p.float().cpu().permute(0, 3, 1, 2), refp)
+    feats = torch.randn(2, 9, 13, 512, generator=g).to(torch.bfloat16)
+    cw = torch.randn(3, 512, generator=g) * 0.05
+    cb = torch.randn(3, generator=g)
+    lg = ops.head_1x1(feats.to(dev), cw.to(dev), cb.to(dev)).cpu()
+    refl = torch.einsum('nhwc,kc->nkhw', feats.float(), cw) + cb.view(1, 3, 1, 1)
+    assert (lg - refl).abs().max() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------- K3 upsample + argmax
+@pytest.mark.parametrize('shape', [(2, 13, 16, 100, 128), (1, 128, 128, 1024, 1024), (1, 77, 128, 611, 1024)])
+def test_upsample_argmax_bit_exact(cuda_device, shape):
+    ops = _ops()
+    N, h, w, H, W = shape
+    rng = np.random.default_rng(h)
+    low = rng.standard_normal((N, 3, h, w)).astype(np.float32)
+    low[0, :, 0, :4] = 0.25            # exact ties -> lowest index must win
+    exp_up = omodel.upsample_bicubic_restated(low, (H, W))
+    t = torch.from_numpy(low).to(cuda_device)
+    up = ops.upsample_bicubic(t, (H, W)).cpu().numpy()
+    assert np.array_equal(up, exp_up), 'upsample differs from the restated f32 specification'
+    mask = ops.upsample_argmax(t, (H, W)).cpu().numpy()
+    assert np.array_equal(mask, omodel.argmax_lowest(exp_up))
+    # against torch's own kernel: float round-off only
+    ref = torch.nn.functional.interpolate(torch.from_numpy(low), size=(H, W), mode='bicubic', align_corners=False)
+    assert np.abs(up - ref.numpy()).max() < 5e-5
+    assert (mask != ref.argmax(1).numpy()).mean() < 1e-4
+
+
+def test_upsample_golden(cuda_device, golden_dir):
+    ops = _ops()
+    g = np.load(os.path.join(golden_dir, 'upsample_argmax.npz'))
+    mask = ops.upsample_argmax(torch.from_numpy(g['lowres']).to(cuda_device), g['up'].shape[-2:]).cpu().numpy()
+    assert (mask != g['mask']).mean() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------- K5 region removal
+def test_ccl_golden(cuda_device, golden_dir):
+    ops = _ops()
+    g = np.load(os.path.join(golden_dir, 'ccl_small.npz'))
+    m = torch.from_numpy(g['mask']).unsqueeze(0).to(cuda_device)
+    out, counts = ops.remove_small_zones_u8(m)
+    assert np.array_equal(out[0].cpu().numpy(), g['out'])
+    assert counts[0].tolist() == np.bincount(g['out'].ravel(), minlength=3).tolist()
+
+
+@pytest.mark.parametrize('shape,thr', [((3, 200, 333), 150), ((1, 1024, 1024), 150), ((2, 611, 1024), 150), ((4, 64, 64), 9)])
+def test_ccl_random_vs_oracle(cuda_device, shape, thr):
+    ops = _ops()
+    N, H, W = shape
+    masks = np.stack([synth.class_mask(H, W, 10 + i) for i in range(N)])
+    rng = np.random.default_rng(1)
+    noise = rng.random(masks.shape) < 0.02               # salt noise: thousands of tiny components and holes
+    masks = np.where(noise, (masks + rng.integers(1, 3, masks.shape)) % 3, masks).astype(np.uint8)
+    exp = opost.remove_small_zones(masks, thr)
+    t = torch.from_numpy(masks).to(cuda_device)
+    out, counts = ops.remove_small_zones_u8(t, thr)
+    got = out.cpu().numpy()
+    assert np.array_equal(got, exp)
+    for i in range(N):
+        assert counts[i].tolist() == np.bincount(exp[i].ravel(), minlength=3).tolist()
+    # exclude_nodes: 2 -> 1 after the removal (models.py:273-276)
+    t2 = torch.from_numpy(masks).to(cuda_device)
+    out2, counts2 = ops.remove_small_zones_u8(t2, thr, exclude_nodes=True)
+    assert np.array_equal(out2.cpu().numpy(), opost.exclude_nodes(exp))
+    assert int(counts2[:, 2].sum()) == 0
+
+
+def test_ccl_edge_cases(cuda_device):
+    ops = _ops()
+    dev = cuda_device
+    for m in (np.zeros((1, 50, 70), np.uint8), np.full((1, 50, 70), 2, np.uint8)):
+        out, counts = ops.remove_small_zones_u8(torch.from_numpy(m.copy()).to(dev))
+        assert np.array_equal(out.cpu().numpy(), opost.remove_small_zones(m))
+    # spiral / snake: one long thin 8-connected component (deep union-find chains)
+    m = np.zeros((1, 128, 128), np.uint8)
+    for r in range(0, 128, 4):
+        m[0, r, :] = 1
+        m[0, r:r + 4, 127 if (r // 4) % 2 == 0 else 0] = 1
+    m[0, 64, 50:60] = 0
+    out, _ = ops.remove_small_zones_u8(torch.from_numpy(m.copy()).to(dev))
+    assert np.array_equal(out.cpu().numpy(), opost.remove_small_zones(m))
+    # drop-in wrapper: int64 tensor, in place, returns the same object (utils.py:135-148)
+    from neuralbarkcalculator_b200 import utils
+    mm = synth.class_mask(90, 100, 3).astype(np.int64)
+    t = torch.from_numpy(mm.copy()).unsqueeze(0).to(dev)
+    r = utils.remove_small_zones(t)
+    assert r is t and np.array_equal(t[0].cpu().numpy(), opost.remove_small_zones_2d(mm))
+
+
+def test_ccl_idempotent_full_size(cuda_device):
+    ops = _ops()
+    m = torch.from_numpy(np.stack([synth.class_mask(1024, 1024, 77 + i) for i in range(4)])).to(cuda_device)
+    a, ca = ops.remove_small_zones_u8(m.clone())
+    b, cb = ops.remove_small_zones_u8(a.clone())
+    assert torch.equal(a, b) and torch.equal(ca, cb)
+    assert int(ca.sum()) == 4 * 1024 * 1024
+
+
+# ------------------------------------------------------------------------------------------------- K4 weighted CE
+def test_wce_golden_and_autograd(cuda_device, golden_dir):
+    ops = _ops()
+    from neuralbarkcalculator_b200 import utils
+    g = np.load(os.path.join(golden_dir, 'wce_small.npz'))
+    dev = cuda_device
+    logits = torch.from_numpy(g['logits']).to(dev)
+    w = torch.from_numpy(g['weights']).to(dev)
+    for tgt in (torch.from_numpy(g['target']).to(dev), torch.from_numpy(g['target']).long().to(dev)):
+        loss, grad = ops.wce_fwd_bwd(logits, tgt, w)
+        assert abs(float(loss) - float(g['loss'])) < 1e-5 * max(1.0, abs(float(g['loss'])))       # f32 tolerance
+        assert np.abs(grad.cpu().numpy() - g['grad']).max() < 1e-7 + 1e-5 * np.abs(g['grad']).max()
+    crit = utils.CustomWeightedCrossEntropy(utils.get_pos_weight())
+    p = logits.clone().requires_grad_(True)
+    out = crit(p, torch.from_numpy(g['target']).long().to(dev))
+    (out * 2).backward()
+    assert out.dim() == 0 and np.abs(p.grad.cpu().numpy() - 2 * g['grad']).max() < 1e-6
+
+
+def test_wce_large_vs_oracle(cuda_device):
+    ops = _ops()
+    gen = torch.Generator().manual_seed(4)
+    logits = torch.randn(2, 3, 512, 768, generator=gen) * 3
+    target = torch.from_numpy(np.stack([synth.class_mask(512, 768, s) for s in (5, 6)])).long()
+    w = torch.tensor(olosses.DEFAULT_WEIGHTS)
+    ref_loss, ref_grad = olosses.custom_weighted_cross_entropy_with_grad(logits, target, w)
+    loss, grad = ops.wce_fwd_bwd(logits.to(cuda_device), target.to(torch.uint8).to(cuda_device), w.to(cuda_device))
+    assert abs(float(loss) - float(ref_loss)) < 2e-5 * abs(float(ref_loss))
+    assert (grad.cpu() - ref_grad).abs().max() < 1e-9 + 2e-5 * ref_grad.abs().max()

@@ -1,0 +1,124 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every symbol of include/nbc.h,
+the Python mirror keeps the reference's interface, and nothing computes without a GPU."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, 'include', 'nbc.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(nbc_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_header_symbol(libnbc):
+    from neuralbarkcalculator_b200 import _lib
+    names = header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(libnbc, n), 'libnbc.so does not export %s' % n
+    assert sorted(_lib.SIGNATURES.keys()) == names, 'ctypes table and include/nbc.h disagree'
+    assert libnbc.nbc_version() == 100
+
+
+def test_no_cpu_fallback(libnbc):
+    from neuralbarkcalculator_b200 import _lib, ops, utils
+    if torch.cuda.is_available():
+        pytest.skip('CPU-only check')
+    assert libnbc.nbc_device_check(0) == -3
+    assert 'no CUDA device' in _lib.last_error()
+    with pytest.raises(RuntimeError):
+        utils.remove_small_zones(torch.zeros(1, 8, 8, dtype=torch.int64))
+    with pytest.raises(RuntimeError):
+        ops.upsample_argmax(torch.zeros(1, 3, 4, 4), (32, 32))
+    with pytest.raises(RuntimeError):
+        utils.CustomWeightedCrossEntropy(utils.get_pos_weight())(torch.zeros(1, 3, 4, 4), torch.zeros(1, 4, 4).long())
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'neuralbarkcalculator_b200')
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith(('.py', '.cu', '.cuh', '.h')):
+                txt = open(os.path.join(dp, fn)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', txt, flags=re.M), fn
+                assert '/root/reference' not in txt, fn
+
+
+def test_model_state_dict_is_drop_in(synthetic_sd):
+    import neuralbarkcalculator_b200 as nbc
+    m = nbc.fcn_resnet50(pretrained=False)
+    assert list(m.state_dict().keys()) == list(synthetic_sd.keys())
+    m.load_state_dict(synthetic_sd, strict=True)
+    assert hasattr(m, 'backbone') and hasattr(m, 'classifier')
+    # torchvision's own FCN-ResNet50 checkpoint layout (num_classes=3, no aux head) is the same key set
+    from torchvision.models.segmentation import fcn_resnet50 as tv_fcn
+    tv = tv_fcn(weights=None, weights_backbone=None, num_classes=3, aux_loss=False)
+    assert set(tv.state_dict().keys()) == set(m.state_dict().keys())
+    m.eval()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 32, 32))       # CPU tensor -> loud failure, not a torch fallback
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 3, 32, 32))
+
+
+def test_dataset_order_matches_reference(golden_dir, tmp_path):
+    from PIL import Image
+    from neuralbarkcalculator_b200 import dataset, predict
+    g = json.load(open(os.path.join(golden_dir, 'dataset_order.json')))
+    for wood, files in g['names'].items():
+        os.makedirs(tmp_path / 'samples' / wood)
+        for fn in files:
+            p = tmp_path / 'samples' / wood / fn
+            if fn.endswith('.txt'):
+                p.write_text('x')
+            else:
+                Image.fromarray(np.zeros((4, 4, 3), np.uint8)).save(p, format='BMP' if fn.lower().endswith('bmp') else 'PNG')
+    items = [(os.path.relpath(a, tmp_path), c, d) for a, b, c, d in dataset.make_dataset_for_dir(str(tmp_path))]
+    assert items == [tuple(x) for x in g['items']]
+    predict.generate_folders(str(tmp_path), False)
+    dirs = sorted(os.path.relpath(os.path.join(dp, d), tmp_path) for dp, dn, _ in os.walk(tmp_path) for d in dn)
+    assert dirs == g['dirs']
+    with pytest.raises(IOError):
+        dataset.make_dataset_for_dir(str(tmp_path / 'nowhere'))
+    os.makedirs(tmp_path / 'empty' / 'samples' / 'sapin')
+    with pytest.raises(RuntimeError):
+        dataset.RegressionDatasetFolder(str(tmp_path / 'empty'))
+
+
+def test_bmp_raw_reader(tmp_path):
+    from oracle import synth
+    from neuralbarkcalculator_b200 import dataset
+    img = synth.texture_u8(8, 12, 1)
+    p = str(tmp_path / 'x.bmp')
+    synth.write_bmp(p, img)
+    buf, H, W, pitch, bgr, bottom_up = dataset.read_bmp_pixels(p)
+    assert (H, W, pitch, bgr, bottom_up) == (8, 12, 36, True, True)
+    dec = buf.reshape(H, pitch)[:, :W * 3].reshape(H, W, 3)[::-1, :, ::-1]
+    assert np.array_equal(dec, img)
+
+
+def test_cli_arguments():
+    from neuralbarkcalculator_b200 import predict
+    a = predict.parse_args(['some/root', '--exclude_nodes'])
+    assert a.root_path == 'some/root' and a.exclude_nodes and not a.only_preprocess and a.device == 'cuda:0'
+    with pytest.raises(SystemExit):
+        predict.parse_args(['some/root', '--device', 'cpu'])
+
+
+def test_stats_strings_match_reference_arithmetic(golden_dir):
+    """The CSV strings computed from integer counts equal the reference's float32 tensor arithmetic."""
+    import neuralbarkcalculator_b200 as nbc
+    g = np.load(os.path.join(golden_dir, 'stats_small.npz'))
+    mask = g['mask']
+    counts = np.bincount(mask.ravel(), minlength=3)
+    calc = nbc.NeuralBarkCalculator.__new__(nbc.NeuralBarkCalculator)
+    calc.mm_per_pix = nbc.NeuralBarkCalculator.DEFAULT_MM_PER_PIXEL
+    assert calc._stats_strings(counts.tolist(), mask.size) == list(g['strings'])

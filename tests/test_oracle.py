@@ -1,0 +1,157 @@
+"""CPU tests: the oracle against the golden fixtures (tests/golden, produced by oracle/make_golden.py from the
+reference's own code) and against independent restatements."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import losses as olosses
+from oracle import model as omodel
+from oracle import pipeline as opipe
+from oracle import postprocess as opost
+from oracle import preprocess as opre
+from oracle import synth
+
+
+def test_model_matches_reference_golden(golden_dir, synthetic_sd):
+    g = np.load(os.path.join(golden_dir, 'model_small.npz'))
+    net = omodel.load_model(synthetic_sd)
+    x = omodel.normalise_u8(g['image'])
+    with torch.no_grad():
+        logits = net(x).numpy()
+    # golden logits come from the reference's models.fcn_resnet50; CPU conv kernels may differ by round-off only
+    assert np.abs(logits - g['logits']).max() < 2e-4
+    agree = (logits.argmax(1) == g['mask']).mean()
+    assert agree > 0.9995
+
+
+def test_state_dict_layout(synthetic_sd):
+    keys = list(synthetic_sd.keys())
+    assert len(keys) == 326
+    assert keys[0] == 'backbone.conv1.weight' and keys[-1] == 'classifier.4.bias'
+    assert sum(v.numel() for k, v in synthetic_sd.items() if 'num_batches' not in k and 'running' not in k) == 32947779
+
+
+def test_upsample_restated_vs_torch(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'upsample_argmax.npz'))
+    up = omodel.upsample_bicubic_restated(g['lowres'], g['up'].shape[-2:])
+    assert np.abs(up - g['up']).max() < 5e-6
+    mism = omodel.argmax_lowest(up) != g['mask']
+    assert mism.mean() < 1e-4
+    # non-integer scale (trimmed image: 77 -> 611) and exact 8x
+    rng = np.random.default_rng(0)
+    for (h, w, H, W) in [(77, 128, 611, 1024), (16, 16, 128, 128)]:
+        low = rng.standard_normal((1, 3, h, w)).astype(np.float32)
+        ref = torch.nn.functional.interpolate(torch.from_numpy(low), size=(H, W), mode='bicubic', align_corners=False)
+        got = omodel.upsample_bicubic_restated(low, (H, W))
+        # torch's vectorised CPU kernel rounds the source index differently at non-integer scales (~1e-5)
+        assert np.abs(got - ref.numpy()).max() < (5e-5 if H % h else 2e-6)
+
+
+def test_wce_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'wce_small.npz'))
+    loss, grad = olosses.custom_weighted_cross_entropy_with_grad(torch.from_numpy(g['logits']),
+                                                                 torch.from_numpy(g['target']).long(),
+                                                                 torch.from_numpy(g['weights']))
+    assert abs(float(loss) - float(g['loss'])) < 1e-6
+    assert np.abs(grad.numpy() - g['grad']).max() < 1e-8
+
+
+def test_wce_gradient_formula():
+    """dL/dlogit = w * (softmax - onehot) / n, w constant w.r.t. autograd."""
+    g = torch.Generator().manual_seed(1)
+    logits = torch.randn(1, 3, 8, 9, generator=g)
+    target = torch.randint(0, 3, (1, 8, 9), generator=g)
+    w = torch.tensor(olosses.DEFAULT_WEIGHTS)
+    _, grad = olosses.custom_weighted_cross_entropy_with_grad(logits, target, w)
+    sm = torch.softmax(logits, 1)
+    onehot = torch.nn.functional.one_hot(target, 3).permute(0, 3, 1, 2).float()
+    cw = w[torch.max(logits.argmax(1), target)].unsqueeze(1)
+    assert torch.allclose(grad, cw * (sm - onehot) / target.numel(), atol=1e-7)
+
+
+def test_preprocess_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'preprocess_small.npz'))
+    raw = g['raw']
+    S = opre.resize4x_S(raw)
+    Sc = np.clip(S, 256 * int(raw.min()), 256 * int(raw.max()))
+    out = ((Sc + 128) >> 8).astype(np.uint8)
+    first, last = opre.trim_rows_from_counts((Sc.sum(-1) >= 66).sum(1), Sc.shape[1], Sc.shape[0])
+    assert (first, last) == (int(g['first']), int(g['last']))
+    assert np.array_equal(out[first:last], g['out'])
+
+
+def test_resize4x_equals_general_cubic():
+    """The integer 4x filter is the Catmull-Rom cubic sampled at 4i+1.5 (general float64 restatement)."""
+    img = synth.texture_u8(64, 96, seed=2)
+    S = opre.resize4x_S(img)
+    f = opre.resize_general_f64(img, 16, 24)
+    lo, hi = float(img.min()), float(img.max())
+    assert np.abs(np.clip(S / 256.0, lo, hi) - f).max() < 1e-9
+
+
+def test_preprocess_full_4096_trim():
+    raw, top, bottom = synth.raw_image_u8(seed=5, size=4096, top=803, bottom=402)
+    out, first, last = opre.preprocess_u8(raw)
+    assert out.shape[1] == 1024 and out.shape[0] == last - first
+    assert abs(first - top / 4) <= 1 and abs(last - (1024 - bottom / 4)) <= 1
+
+
+def test_trim_all_dark_and_non_square():
+    img = np.zeros((64, 64, 3), np.uint8)
+    out, first, last = opre.preprocess_u8(img)
+    assert (first, last) == (0, 64) and out.shape[0] == 64      # nothing kept -> argmax of all False -> full image
+    img = synth.texture_u8(40, 64, 1)
+    img[:10] = 0
+    out, first, last = opre.preprocess_u8(img)
+    assert out.shape[0] == 40                                    # not square -> not trimmed (models.py:200)
+
+
+def test_ccl_golden_and_bruteforce(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'ccl_small.npz'))
+    assert np.array_equal(opost.remove_small_zones_2d(g['mask']), g['out'])
+    rng = np.random.default_rng(3)
+    for _ in range(3):
+        m = (rng.random((40, 56)) < 0.45).astype(np.uint8) * rng.integers(1, 3, (40, 56)).astype(np.uint8)
+        assert np.array_equal(opost.remove_small_zones_2d(m, 12), opost.remove_small_zones_bruteforce(m, 12))
+
+
+def test_ccl_threshold_is_strict():
+    m = np.zeros((40, 40), np.uint8)
+    m[2:12, 2:17] = 1          # 150 px: kept (size < 150 is strict)
+    m[20:30, 2:17] = 1
+    m[29, 16] = 0              # 149 px: removed
+    out = opost.remove_small_zones_2d(m)
+    assert out[5, 5] == 1 and out[25, 5] == 0
+
+
+def test_stats_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'stats_small.npz'))
+    assert list(g['strings']) == opost.class_stats_strings(g['mask'])
+
+
+def test_dataset_order_golden(golden_dir, tmp_path):
+    g = json.load(open(os.path.join(golden_dir, 'dataset_order.json')))
+    from PIL import Image
+    for wood, files in g['names'].items():
+        os.makedirs(tmp_path / 'samples' / wood)
+        for fn in files:
+            p = tmp_path / 'samples' / wood / fn
+            if fn.endswith('.txt'):
+                p.write_text('x')
+            else:
+                Image.fromarray(np.zeros((4, 4, 3), np.uint8)).save(p, format='BMP' if fn.lower().endswith('bmp') else 'PNG')
+    items = [(os.path.relpath(a, tmp_path), b, c) for a, b, c in opipe.make_dataset_for_dir(str(tmp_path))]
+    assert items == [tuple(x) for x in g['items']]
+    opipe.generate_folders(str(tmp_path))
+    dirs = sorted(os.path.relpath(os.path.join(dp, d), tmp_path) for dp, dn, _ in os.walk(tmp_path) for d in dn)
+    assert dirs == g['dirs']
+
+
+def test_bmp_roundtrip(tmp_path):
+    img = synth.texture_u8(12, 10, 0)       # width 10 -> row padding
+    p = str(tmp_path / 'a.bmp')
+    synth.write_bmp(p, img)
+    assert np.array_equal(opipe.load_rgb(p), img)
