@@ -1,0 +1,286 @@
+"""bench.py -- headline benchmark of the B200 segmentation hot path (see the contract in DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload predict64|batch32]
+
+workload predict64 (default, BASELINE.json configs[1]): a "step" is one pass of the predict hot path over a batch
+of 64 synthetic raw 4096x4096x3 scans (BMP pixel arrays: BGR, bottom-up, dark bands) with --exclude_nodes:
+K1 resize+trim -> FCN-ResNet50 (bf16, tcgen05) -> K3 upsample+argmax -> K5 region removal + class counts.
+  value : images/s, raw scans resident in HBM when the timed region starts (3.2 GB per rank, >> the 126 MB L2)
+  e2e   : images/s through PredictEngine.run_host: pinned host buffers in (50 MB H2D per image, inside the timed
+          region), masks + counts copied back to pinned host memory
+workload batch32 (configs[2]): model-only, u8 [32,1024,1024,3] -> mask + counts.
+--impl reference times the CPU oracle (restated reference path, torch CPU f32 with all host threads) on a bounded
+sample: one image per step.  Multi-GPU: one process per GPU (torchrun), images sharded, no collective on the data
+path; time = max over ranks."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RAW = 4096
+BATCH = 64
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='predict64', choices=['predict64', 'batch32'])
+    ap.add_argument('--batch', type=int, default=0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('hbm_gbs', 6650.0), d.get('bf16_tflops_sustained', d.get('bf16_tflops', 1590.0)), 'measured'
+    return 6650.0, 1590.0, 'fallback'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------- synthetic data
+def synth_raw_gpu(n, dev, seed0):
+    """n raw scans as BMP pixel arrays (BGR, bottom-up) in HBM: correlated texture + exact-zero dark bands."""
+    g = torch.Generator(device=dev)
+    mean = torch.tensor([0.4401, 0.6139, 0.7399], device=dev).view(1, 1, 3)   # BGR order
+    std = torch.tensor([0.1271, 0.1272, 0.1068], device=dev).view(1, 1, 3)
+    raws, bands = [], []
+    for i in range(n):
+        g.manual_seed(seed0 + i)
+        lo = torch.randn(1, 3, RAW // 64, RAW // 64, generator=g, device=dev)
+        f = torch.nn.functional.interpolate(lo, size=(RAW, RAW), mode='bicubic', align_corners=False)[0].permute(1, 2, 0)
+        f = f + 0.35 * torch.randn(RAW, RAW, 3, generator=g, device=dev)
+        img = ((mean + std * f) * 255.0).clamp_(0, 255).round_().to(torch.uint8)
+        rng = np.random.default_rng(seed0 + i)
+        top, bottom = int(rng.integers(400, 1201)), int(rng.integers(400, 1201))
+        img[:bottom] = 0              # memory is bottom-up: the first rows in memory are the bottom of the picture
+        img[RAW - top:] = 0
+        raws.append(img.view(-1).contiguous())
+        bands.append((top, bottom))
+        del f, lo
+    return raws, bands
+
+
+def synth_processed_cpu(seed, rows=None):
+    from oracle import synth
+    raw, top, bottom = synth.raw_image_u8(seed, RAW)
+    return raw
+
+
+# ---------------------------------------------------------------------------------------------------- reference arm
+def time_reference(steps, warmup, sd):
+    """CPU oracle (restated reference predict path, f32, eval) on one 4096^2 scan per step, all host threads."""
+    from oracle import model as omodel, postprocess as opost, preprocess as opre, synth
+    torch.set_num_threads(os.cpu_count())
+    net = omodel.load_model(sd)
+    times = []
+    for s in range(warmup + steps):
+        raw, _, _ = synth.raw_image_u8(1000 + s, RAW)
+        t0 = time.perf_counter()
+        proc, _, _ = opre.preprocess_u8(raw)
+        x = omodel.normalise_u8(proc)
+        with torch.no_grad():
+            logits = net(x)
+        mask = torch.argmax(logits, dim=1)[0].numpy()
+        mask = opost.exclude_nodes(opost.remove_small_zones_2d(mask))
+        opost.class_stats_strings(mask)
+        t1 = time.perf_counter()
+        if s >= warmup:
+            times.append(t1 - t0)
+    return len(times) / sum(times), times
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    from oracle import model as omodel
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'model_small.npz'))
+    sd = omodel.synthetic_state_dict(seed=0, head=(g['head_w'], g['head_b']))
+    workload = ('predict.py --exclude_nodes hot path on %d synthetic 4096x4096 raw scans per GPU (K1 resize+trim, '
+                'FCN-ResNet50 3-class random-init, K3 upsample+argmax, K5 <150px region removal + counts)' % BATCH)
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        v, times = time_reference(args.steps, args.warmup, sd)
+        line = {'impl': 'reference', 'metric': 'images/sec', 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * float(np.mean(times)),
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': workload, 'sample': '1 image per step'},
+                'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': os.cpu_count(), 'kind': 'port',
+                                 'sample': '%d timed steps of 1 synthetic 4096^2 scan each through the CPU oracle '
+                                           '(restated reference predict path without the matplotlib figure / PNG IO)' % args.steps},
+                'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return
+
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    import neuralbarkcalculator_b200 as nbc
+    from neuralbarkcalculator_b200 import _lib, engine
+
+    calc = nbc.NeuralBarkCalculator(None, str(dev), state_dict=sd)
+    eng = engine.PredictEngine(calc.model, dev)
+    hbm_peak, tf_peak, peak_kind = peaks()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    if args.workload == 'batch32':
+        B = args.batch or 32
+        from oracle import synth
+        imgs = torch.from_numpy(np.stack([synth.texture_u8(1024, 1024, 100 * rank + i) for i in range(min(B, 4))])).to(dev)
+        imgs = imgs.repeat((B + imgs.shape[0] - 1) // imgs.shape[0], 1, 1, 1)[:B].contiguous()
+        from neuralbarkcalculator_b200 import ops
+
+        def step():
+            mask = calc.model.predict_mask_u8(imgs)
+            ops.remove_small_zones_u8(mask, 150, exclude_nodes=True)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        ms, launches = timed(step, args.steps, args.warmup)
+        clocks = sampler.summary()
+        n_img = B
+        workload = 'model-only batched inference: u8 [%d,1024,1024,3] -> mask + counts (configs[2])' % B
+        e2e = None
+    else:
+        B = args.batch or BATCH
+        raws, _ = synth_raw_gpu(B, dev, 10000 * rank)
+        torch.cuda.synchronize()
+
+        def step():
+            eng.run_device(raws, bgr=True, bottom_up=True, exclude_nodes=True)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        ms, launches = timed(step, args.steps, args.warmup)
+        clocks = sampler.summary()
+        n_img = B
+        e2e = None
+        if not args.no_e2e:
+            host = [torch.empty(RAW * RAW * 3, dtype=torch.uint8).pin_memory() for _ in range(B)]
+            for h, r in zip(host, raws):
+                h.copy_(r)
+            masks_host = [torch.empty(1024 * 1024, dtype=torch.uint8).pin_memory() for _ in range(B)]
+            res = {}
+
+            def step_host():
+                res['rows'], res['counts'], _ = eng.run_host(host, masks_host, bgr=True, bottom_up=True, exclude_nodes=True)
+            ms_h, _ = timed(step_host, args.steps, max(1, args.warmup))
+            d2h = int(sum(r * 1024 for r in res['rows']) + B * 12 + B * 8)
+            e2e = {'value': world * B * args.steps / (ms_h / 1000.0), 'unit': 'images/s',
+                   'h2d_bytes_per_step': B * RAW * RAW * 3, 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_h / args.steps}
+
+    value = world * n_img * args.steps / (ms / 1000.0)
+
+    # roofline of the dominant kernel (conv_tc): per-layer CUDA events over one forward of a representative image
+    roof = None
+    cpu_base = None
+    if rank == 0:
+        from oracle import synth
+        prof_img = torch.from_numpy(synth.texture_u8(624, 1024, 5)).unsqueeze(0).to(dev)
+        plan = calc.model.native_plan()
+        plan.profile(prof_img)
+        layers = plan.profile(prof_img)
+        conv = [(m, f) for (m, f) in layers[2:-1]]
+        conv_ms, conv_fl = sum(m for m, _ in conv), sum(f for _, f in conv)
+        tot_ms = sum(m for m, _ in layers)
+        achieved = conv_fl / (conv_ms * 1e-3) / 1e12
+        roof = {'bound': 'tensor', 'achieved': achieved, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf_peak,
+                'traffic': None, 'peak_kind': peak_kind + ' (sustained bf16)',
+                'kernel': 'conv_tc_kernel (53 launches per image, per-layer CUDA events, 624x1024 image)',
+                'conv_share_of_forward': conv_ms / tot_ms, 'forward_ms': tot_ms}
+        if not args.no_cpu_baseline and world == 1:
+            v, times = time_reference(3, 1, sd)
+            cpu_base = {'value': v, 'unit': 'images/s', 'cores': os.cpu_count(), 'kind': 'port',
+                        'sample': '3 synthetic 4096^2 scans through the CPU oracle after 1 warm-up (restated reference '
+                                  'predict path; no matplotlib figure, no file IO)'}
+    if rank == 0:
+        line = {'metric': 'images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+                'config': {'workload': workload, 'images_per_step_per_gpu': n_img, 'parallelism': 'dp%d (images sharded, no collective)' % world,
+                           'l2': 'inputs (%.1f GB per rank) larger than L2; no flush needed' % (n_img * RAW * RAW * 3 / 1e9)},
+                'clocks': clocks, 'gpu_launches': launches, 'e2e': e2e, 'roofline': roof, 'cpu_baseline': cpu_base}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
