@@ -104,7 +104,7 @@ def synth_raw_gpu(n, dev, seed0):
         top, bottom = int(rng.integers(400, 1201)), int(rng.integers(400, 1201))
         img[:bottom] = 0              # memory is bottom-up: the first rows in memory are the bottom of the picture
         img[RAW - top:] = 0
-        raws.append(img.view(-1).contiguous())
+        raws.append(img.contiguous().view(-1))
         bands.append((top, bottom))
         del f, lo
     return raws, bands

@@ -6,6 +6,8 @@
 // Layer list (55 convs): stem 7x7/2 (CUDA-core f32, fused normalise) -> maxpool -> 16 bottlenecks
 // (conv1 1x1 +ReLU, conv2 3x3 stride/dilation +ReLU, conv3 1x1 + residual + ReLU, optional downsample 1x1)
 // -> FCNHead conv3x3 + ReLU -> 1x1 (512 -> 3) + bias as f32 planar logits.
+#include <map>
+#include <tuple>
 #include <vector>
 
 #include "common.cuh"
@@ -48,13 +50,10 @@ struct nbc_plan {
   float* cls_b = nullptr;
   std::vector<void*> allocs;
   int impl = 0;
-  // cached launch list
-  int cN = 0, cH = 0, cW = 0, cimpl = -1;
-  void* cws = nullptr;
-  const void* cimg = nullptr;
-  int ckind = -1;
-  float* clogits = nullptr;
-  std::vector<nbc::Step> steps;
+  // cached launch lists (tensor maps are encoded once per shape / workspace): key = (N, H, W, workspace, impl)
+  typedef std::tuple<int, int, int, void*, int> Key;
+  std::map<Key, std::vector<nbc::Step>> cache;
+  std::vector<nbc::Step>* steps_ptr = nullptr;
 };
 
 namespace nbc {
@@ -116,13 +115,15 @@ static int add_conv(nbc_plan* p, const ConvLayer& L, int N, int H, int W, const 
     return NBC_ERR_INVALID;
   }
   *Ho = s.g.Ho(), *Wo = s.g.Wo();
-  p->steps.push_back(s);
+  p->steps_ptr->push_back(s);
   return 0;
 }
 
-static int build_steps(nbc_plan* p, const void* images, int input_kind, int N, int H, int W, float* logits,
-                       void* workspace) {
-  p->steps.clear();
+static int build_steps(nbc_plan* p, int N, int H, int W, void* workspace) {
+  std::vector<Step>& steps = *p->steps_ptr;
+  steps.clear();
+  const void* images = nullptr;   // the stem input and the logits output are patched in at run time
+  float* logits = nullptr;
   size_t big, small;
   buffer_sizes(N, H, W, &big, &small);
   char* ws = reinterpret_cast<char*>(workspace);
@@ -134,15 +135,15 @@ static int build_steps(nbc_plan* p, const void* images, int input_kind, int N, i
   {
     Step s;
     memset(&s.prep, 0, sizeof(s.prep));
-    s.kind = input_kind == 1 ? 5 : 0, s.g = ConvGeom{N, H, W, 3, 64, 7, 7, 2, 3, 1, 1}, s.x = images, s.y = bufB;
+    s.kind = 0, s.g = ConvGeom{N, H, W, 3, 64, 7, 7, 2, 3, 1, 1}, s.x = images, s.y = bufB;
     s.name = "stem";
     s.w = p->stem_w, s.bias = p->stem_b, s.residual = nullptr;
-    p->steps.push_back(s);
+    steps.push_back(s);
     Step m;
     memset(&m.prep, 0, sizeof(m.prep));
     m.kind = 1, m.g = ConvGeom{N, d.H2, d.W2, 64, 64, 3, 3, 2, 1, 1, 0}, m.x = bufB, m.y = bufA, m.name = "maxpool";
     m.w = nullptr, m.bias = nullptr, m.residual = nullptr;
-    p->steps.push_back(m);
+    steps.push_back(m);
   }
   int h = d.H4, w = d.W4;
   void* in = bufA;
@@ -177,23 +178,24 @@ static int build_steps(nbc_plan* p, const void* images, int input_kind, int N, i
   memset(&s.prep, 0, sizeof(s.prep));
   s.kind = 4, s.g = ConvGeom{N, hh, wh, 512, 3, 1, 1, 1, 0, 1, 0}, s.x = t1, s.y = logits, s.name = "head1x1";
   s.w = p->cls_w, s.bias = p->cls_b, s.residual = nullptr;
-  p->steps.push_back(s);
+  steps.push_back(s);
   return 0;
 }
 
-static int run_step(nbc_plan* p, const Step& s, cudaStream_t stream) {
+static int run_step(nbc_plan* p, const Step& s, const void* input, int input_kind, float* logits,
+                    cudaStream_t stream) {
   switch (s.kind) {
     case 0:
-      return nbc_stem_u8(reinterpret_cast<const uint8_t*>(s.x), s.g.N, s.g.H, s.g.W, p->mean, p->std, p->stem_w,
+      if (input_kind == 1)
+        return nbc_stem_f32(reinterpret_cast<const float*>(input), s.g.N, s.g.H, s.g.W, p->stem_w, p->stem_b, s.y,
+                            stream);
+      return nbc_stem_u8(reinterpret_cast<const uint8_t*>(input), s.g.N, s.g.H, s.g.W, p->mean, p->std, p->stem_w,
                          p->stem_b, s.y, stream);
-    case 5:
-      return nbc_stem_f32(reinterpret_cast<const float*>(s.x), s.g.N, s.g.H, s.g.W, p->stem_w, p->stem_b, s.y, stream);
     case 1: return nbc_maxpool3x3s2_bf16(s.x, s.g.N, s.g.H, s.g.W, 64, s.y, stream);
     case 2: return conv_tc_run(&s.prep, stream);
     case 3: return conv_mma(s.g, s.x, s.w, s.bias, s.residual, s.y, stream);
     case 4:
-      return nbc_head_1x1(s.x, (int64_t)s.g.H * s.g.W, s.g.N, 512, p->cls_w, p->cls_b, reinterpret_cast<float*>(s.y),
-                          stream);
+      return nbc_head_1x1(s.x, (int64_t)s.g.H * s.g.W, s.g.N, 512, p->cls_w, p->cls_b, logits, stream);
   }
   return NBC_ERR_INVALID;
 }
@@ -208,15 +210,20 @@ static int ensure_steps(nbc_plan* p, const void* images, int input_kind, int N, 
     return NBC_ERR_WORKSPACE;
   }
   NBC_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 1024 == 0, "nbc_plan_forward: workspace must be 1024-byte aligned");
-  if (p->cN != N || p->cH != H || p->cW != W || p->cws != workspace || p->cimg != images || p->clogits != logits ||
-      p->cimpl != p->impl || p->ckind != input_kind) {
-    int rc = build_steps(p, images, input_kind, N, H, W, logits, workspace);
-    if (rc) {
-      p->cN = 0;
-      return rc;
-    }
-    p->cN = N, p->cH = H, p->cW = W, p->cws = workspace, p->cimg = images, p->clogits = logits, p->cimpl = p->impl;
-    p->ckind = input_kind;
+  (void)images, (void)logits;
+  nbc_plan::Key key(N, H, W, workspace, p->impl);
+  auto it = p->cache.find(key);
+  if (it != p->cache.end()) {
+    p->steps_ptr = &it->second;
+    return 0;
+  }
+  if (p->cache.size() >= 256) p->cache.clear();
+  p->steps_ptr = &p->cache[key];
+  int rc = build_steps(p, N, H, W, workspace);
+  if (rc) {
+    p->cache.erase(key);
+    p->steps_ptr = nullptr;
+    return rc;
   }
   return 0;
 }
@@ -324,8 +331,8 @@ extern "C" int nbc_plan_forward(nbc_plan* p, const void* input, int input_kind, 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   int rc = ensure_steps(p, input, input_kind, N, H, W, lowres_logits, workspace, workspace_bytes);
   if (rc) return rc;
-  for (const Step& s : p->steps) {
-    rc = run_step(p, s, stream);
+  for (const Step& s : *p->steps_ptr) {
+    rc = run_step(p, s, input, input_kind, lowres_logits, stream);
     if (rc) return rc;
   }
   return 0;
@@ -337,20 +344,21 @@ extern "C" int nbc_plan_profile(nbc_plan* p, const void* input, int input_kind, 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   int rc = ensure_steps(p, input, input_kind, N, H, W, lowres_logits, workspace, workspace_bytes);
   if (rc) return rc;
-  const int n = (int)p->steps.size();
+  const std::vector<Step>& steps = *p->steps_ptr;
+  const int n = (int)steps.size();
   NBC_REQUIRE(ms_out && max_layers >= n, "nbc_plan_profile: need room for %d layers", n);
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) NBC_CUDA(cudaEventCreate(&e));
   NBC_CUDA(cudaEventRecord(ev[0], stream));
   for (int i = 0; i < n; ++i) {
-    rc = run_step(p, p->steps[i], stream);
+    rc = run_step(p, steps[i], input, input_kind, lowres_logits, stream);
     if (rc) return rc;
     NBC_CUDA(cudaEventRecord(ev[i + 1], stream));
   }
   NBC_CUDA(cudaStreamSynchronize(stream));
   for (int i = 0; i < n; ++i) {
     NBC_CUDA(cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]));
-    if (flops_out) flops_out[i] = (p->steps[i].kind == 1) ? 0.0 : p->steps[i].g.flops();
+    if (flops_out) flops_out[i] = (steps[i].kind == 1) ? 0.0 : steps[i].g.flops();
   }
   for (auto& e : ev) cudaEventDestroy(e);
   return n;

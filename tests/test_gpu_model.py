@@ -72,7 +72,7 @@ def test_model_full_size_vs_oracle(cuda_device, synthetic_sd):
         t = torch.from_numpy(img).unsqueeze(0).to(cuda_device)
         low = m.lowres_logits_u8(t).cpu().numpy()
         err = _report('%dx%d' % (H, W), low, ref_low.numpy())
-            mask = m.predict_mask_u8(t).cpu().numpy()[0]
+        mask = m.predict_mask_u8(t).cpu().numpy()[0]
         ref_mask = ref_mask[0].numpy()
         agree = (mask == ref_mask).mean()
         top2 = ref_up.topk(2, dim=1).values
