@@ -83,6 +83,14 @@ int nbc_stem_u8(const uint8_t* img, int N, int H, int W, const float* mean3_host
 /* same conv on an already normalised f32 NCHW tensor [N,3,H,W] (what nn.Module.forward receives, models.py:33) */
 int nbc_stem_f32(const float* x_nchw, int N, int H, int W, const float* w_stem, const float* bias, void* out,
                  void* stream);
+/* tensor-core stem (what the plan uses): the image is staged as zero-padded normalised bf16 [N][Hp][Wp][4] in the
+ * workspace and the 7x7/2 conv runs as an implicit GEMM (K = 7 rows x 8 px x 4 ch = 224) on tcgen05.
+ * w224: bf16 [64][7][8][4] from nbc_stem_pack_weights(w_stem f32 [64][7][7][3] BN-folded). */
+size_t nbc_stem_tc_workspace_bytes(int N, int H, int W);
+int nbc_stem_pack_weights(const float* w_stem_f32, void* w224_bf16, void* stream);
+int nbc_stem_tc(const void* input, int input_kind, int N, int H, int W, const float* mean3_host,
+                const float* std3_host, const void* w224_bf16, const float* bias, void* workspace,
+                size_t workspace_bytes, void* out, void* stream);
 int nbc_maxpool3x3s2_bf16(const void* x, int N, int H, int W, int C, void* y, void* stream);
 
 /* ---- head tail: Dropout(eval)=identity + Conv2d(512,3,1)+bias  (models.py:113-124) -> f32 planar logits ------ */

@@ -26,6 +26,10 @@ SIGNATURES = {
     'nbc_conv_bf16': (c_int, [C.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'nbc_stem_u8': (c_int, [c_void_p, c_int, c_int, c_int, C.POINTER(c_float), C.POINTER(c_float), c_void_p, c_void_p, c_void_p, c_void_p]),
     'nbc_stem_f32': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'nbc_stem_tc_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'nbc_stem_pack_weights': (c_int, [c_void_p, c_void_p, c_void_p]),
+    'nbc_stem_tc': (c_int, [c_void_p, c_int, c_int, c_int, c_int, C.POINTER(c_float), C.POINTER(c_float), c_void_p, c_void_p,
+                    c_void_p, c_size_t, c_void_p, c_void_p]),
     'nbc_maxpool3x3s2_bf16': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'nbc_head_1x1': (c_int, [c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'nbc_upsample_argmax': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

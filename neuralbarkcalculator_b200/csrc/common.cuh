@@ -179,13 +179,16 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // 8-row swizzle atoms 1024 B apart (SBO).  Bit layout (cf. PTX ISA "tcgen05 matrix descriptor"):
 //   [0,14) start address >> 4 | [16,30) LBO >> 4 (ignored for swizzled K-major, set to 1)
 //   [32,46) SBO >> 4 | [46,48) version = 1 (sm_100) | [61,64) layout type: 2 = SWIZZLE_128B
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+// kSwizzleBytes = 128: rows of 128 B, atoms 1024 B, layout 2; kSwizzleBytes = 64: rows of 64 B, atoms 512 B, layout 4.
+template <uint32_t kSwizzleBytes>
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
+  static_assert(kSwizzleBytes == 128 || kSwizzleBytes == 64, "unsupported swizzle");
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)((8 * kSwizzleBytes) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(kSwizzleBytes == 128 ? 2 : 4) << 61;
   return d;
 }
 // Instruction descriptor for kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), both K-major,

@@ -24,6 +24,9 @@ bool conv_tc_supported(const ConvGeom& g);
 int conv_tc_prepare(const ConvGeom& g, const void* x, const void* w, const float* bias, const void* residual, void* y,
                     ConvTcPrepared* out);
 int conv_tc_run(const ConvTcPrepared* prep, cudaStream_t stream);
+// stem 7x7/2 as an implicit GEMM over the padded bf16 image (see stem.cu)
+int conv_tc_prepare_stem(int N, int Ho, int Wo, int Hp, int Wp, const void* padded, const void* w224, const float* bias,
+                         void* y, ConvTcPrepared* out);
 int conv_tc(const ConvGeom& g, const void* x, const void* w, const float* bias, const void* residual, void* y,
             cudaStream_t stream);
 
@@ -31,6 +34,10 @@ int conv_tc(const ConvGeom& g, const void* x, const void* w, const float* bias, 
 bool conv_mma_supported(const ConvGeom& g);
 int conv_mma(const ConvGeom& g, const void* x, const void* w, const float* bias, const void* residual, void* y,
              cudaStream_t stream);
+
+// stem staging pass (stem.cu): input (0 = u8 NHWC, 1 = f32 NCHW) -> zero-padded normalised bf16 [N][Hp][Wp][4]
+int stem_tc_pad(const void* input, int input_kind, int N, int H, int W, const float* mean3, const float* std3, void* padded,
+                cudaStream_t stream);
 
 // BN fold + pack (api.cu): w f32 OIHW -> bf16 (and/or f32) [Cout][kh][kw][cin_pad], bias f32[Cout]
 int fold_pack(const float* w, const float* gamma, const float* beta, const float* mean, const float* var,

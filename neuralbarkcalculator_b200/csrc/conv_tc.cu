@@ -37,20 +37,26 @@ struct ConvTcParams {
 };
 
 constexpr int kTcThreads = 192;
-constexpr int kABytes = 128 * 128;  // 128 pixels x 64 bf16
 
-template <int BN>
+// BN = output channels per tile, KBLK = K elements per pipeline stage: 64 (128-byte swizzle) for the bottleneck /
+// head convs, 32 (64-byte swizzle) for the stem, whose K block is one 7-tap row of 8 pixels x 4 channels.
+template <int BN, int KBLK>
 struct TcCfg {
-  static constexpr int kBBytes = BN * 128;
+  static constexpr int kABytes = 128 * KBLK * 2;  // 128 pixels x KBLK bf16
+  static constexpr int kBBytes = BN * KBLK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+  static constexpr int kSmemBytes = (kStages * kStageBytes + 1024 /*barriers*/ + 1024 /*alignment slack*/) < 120 * 1024
+                                        ? 120 * 1024  /* > half an SM: keeps one CTA (one TMEM owner) per SM */
+                                        : (kStages * kStageBytes + 2048);
+  static constexpr uint32_t kSwizzleBytes = KBLK * 2;  // 128 or 64
 };
 
-template <int BN>
+template <int BN, int KBLK>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, KBLK>;
+  constexpr int kABytes = Cfg::kABytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -105,8 +111,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + (int)stage);
             uint8_t* sA = smem + stage * Cfg::kStageBytes;
             mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_4d(sA, mA, &full_bar[stage], cb * 64, cw, ch, img);
-            tma_load_2d(sA + kABytes, &p.tmB, &full_bar[stage], (tap * p.cblocks + cb) * 64, n0);
+            tma_load_4d(sA, mA, &full_bar[stage], cb * KBLK, cw, ch, img);
+            tma_load_2d(sA + kABytes, &p.tmB, &full_bar[stage], (tap * p.cblocks + cb) * KBLK, n0);
             if (++stage == Cfg::kStages) {
               stage = 0;
               phase ^= 1u;
@@ -131,9 +137,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                      (uint32_t)((kb | k) != 0));
+          for (int k = 0; k < KBLK / 16; ++k) {
+            umma_bf16(d_tmem, umma_desc_kmajor<Cfg::kSwizzleBytes>(a_addr + k * 32),
+                      umma_desc_kmajor<Cfg::kSwizzleBytes>(b_addr + k * 32), idesc, (uint32_t)((kb | k) != 0));
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) {
@@ -224,7 +230,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 // host side
 // ------------------------------------------------------------------------------------------------------------
 static int encode_act_map(CUtensorMap* m, const void* base, uint64_t C, uint64_t Wd, uint64_t Hd, uint64_t Nd,
-                          uint64_t strideW, uint64_t strideH, uint64_t strideN, uint32_t boxW, uint32_t boxH) {
+                          uint64_t strideW, uint64_t strideH, uint64_t strideN, uint32_t boxW, uint32_t boxH,
+                          uint32_t boxC = 64) {
   encode_tiled_fn enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -232,11 +239,11 @@ static int encode_act_map(CUtensorMap* m, const void* base, uint64_t C, uint64_t
   }
   cuuint64_t dims[4] = {C, Wd, Hd, Nd};
   cuuint64_t strides[3] = {strideW, strideH, strideN};
-  cuuint32_t box[4] = {64, boxW, boxH, 1};
+  cuuint32_t box[4] = {boxC, boxW, boxH, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, boxC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(activation) failed: %d (C=%llu W=%llu H=%llu N=%llu box=%ux%u)", (int)r,
               (unsigned long long)C, (unsigned long long)Wd, (unsigned long long)Hd, (unsigned long long)Nd, boxW, boxH);
@@ -245,7 +252,8 @@ static int encode_act_map(CUtensorMap* m, const void* base, uint64_t C, uint64_t
   return 0;
 }
 
-static int encode_weight_map(CUtensorMap* m, const void* base, uint64_t K, uint64_t Cout, uint32_t boxN) {
+static int encode_weight_map(CUtensorMap* m, const void* base, uint64_t K, uint64_t Cout, uint32_t boxN,
+                             uint32_t boxK = 64) {
   encode_tiled_fn enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -253,11 +261,11 @@ static int encode_weight_map(CUtensorMap* m, const void* base, uint64_t K, uint6
   }
   cuuint64_t dims[2] = {K, Cout};
   cuuint64_t strides[1] = {K * 2};
-  cuuint32_t box[2] = {64, boxN};
+  cuuint32_t box[2] = {boxK, boxN};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, boxK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(weights) failed: %d (K=%llu Cout=%llu)", (int)r, (unsigned long long)K,
               (unsigned long long)Cout);
@@ -280,31 +288,37 @@ static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b
 struct ConvTcLaunch {
   ConvTcParams p;
   int block_n;
+  int kblk;
   int grid;
 };
 
-static int build_launch(const ConvGeom& g, const void* x, const void* w, const float* bias, const void* residual,
-                        void* y, ConvTcLaunch* L) {
-  ConvTcParams& p = L->p;
-  memset(&p, 0, sizeof(p));
-  const int Ho = g.Ho(), Wo = g.Wo();
-  // 128-pixel rectangle: fewest tiles, widest on ties
+// 128-pixel output rectangle: fewest tiles, widest on ties
+static void choose_tile(int Ho, int Wo, ConvTcParams* p) {
   int best_tw = 128, best_tiles = INT32_MAX;
   for (int tw = 128; tw >= 8; tw >>= 1) {
     const int th = 128 / tw;
     const int tiles = ceil_div(Wo, tw) * ceil_div(Ho, th);
     if (tiles < best_tiles) best_tiles = tiles, best_tw = tw;
   }
-  p.tw = best_tw;
-  p.th = 128 / best_tw;
-  p.tw_log2 = 0;
-  while ((1 << p.tw_log2) < p.tw) ++p.tw_log2;
-  p.tiles_w = ceil_div(Wo, p.tw);
-  p.tiles_h = ceil_div(Ho, p.th);
+  p->tw = best_tw;
+  p->th = 128 / best_tw;
+  p->tw_log2 = 0;
+  while ((1 << p->tw_log2) < p->tw) ++p->tw_log2;
+  p->tiles_w = ceil_div(Wo, p->tw);
+  p->tiles_h = ceil_div(Ho, p->th);
+}
+
+static int build_launch(const ConvGeom& g, const void* x, const void* w, const float* bias, const void* residual,
+                        void* y, ConvTcLaunch* L) {
+  ConvTcParams& p = L->p;
+  memset(&p, 0, sizeof(p));
+  const int Ho = g.Ho(), Wo = g.Wo();
+  choose_tile(Ho, Wo, &p);
   p.N = g.N, p.Ho = Ho, p.Wo = Wo, p.Cout = g.Cout;
   p.num_m_tiles = g.N * p.tiles_w * p.tiles_h;
   const int bn = (g.Cout % 256 == 0) ? 256 : (g.Cout % 128 == 0 ? 128 : 64);
   L->block_n = bn;
+  L->kblk = 64;
   p.num_n_tiles = g.Cout / bn;
   p.n_taps = g.kh * g.kw;
   p.cblocks = g.Cin / 64;
@@ -358,15 +372,48 @@ static int build_launch(const ConvGeom& g, const void* x, const void* w, const f
   return 0;
 }
 
-template <int BN>
+template <int BN, int KBLK>
 static int launch_bn(const ConvTcLaunch& L, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    NBC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::kSmemBytes));
+    NBC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TcCfg<BN, KBLK>::kSmemBytes));
     attr_set = true;
   }
-  conv_tc_kernel<BN><<<L.grid, kTcThreads, TcCfg<BN>::kSmemBytes, stream>>>(L.p);
+  conv_tc_kernel<BN, KBLK><<<L.grid, kTcThreads, TcCfg<BN, KBLK>::kSmemBytes, stream>>>(L.p);
   NBC_CHECK_LAUNCH();
+  return 0;
+}
+
+// Stem as an implicit GEMM (see stem.cu): A = the zero-padded, normalised bf16 image [N][Hp][Wp][4]; one K block is
+// tap row ky = 8 consecutive pixels x 4 channels (32 elements, 64 B) starting at padded pixel (2*ho + ky, 2*wo).
+// The windows of neighbouring outputs overlap (stride 16 B, extent 64 B): the tensor map simply describes that
+// address function.  Even / odd padded rows are two lattices, exactly like the stride-2 convolutions.
+int conv_tc_prepare_stem(int N, int Ho, int Wo, int Hp, int Wp, const void* padded, const void* w224, const float* bias,
+                         void* y, ConvTcPrepared* out) {
+  ConvTcLaunch* L = reinterpret_cast<ConvTcLaunch*>(out->storage);
+  ConvTcParams& p = L->p;
+  memset(&p, 0, sizeof(p));
+  choose_tile(Ho, Wo, &p);
+  p.N = N, p.Ho = Ho, p.Wo = Wo, p.Cout = 64;
+  p.num_m_tiles = N * p.tiles_w * p.tiles_h;
+  p.num_n_tiles = 1;
+  p.n_taps = 7, p.cblocks = 1, p.relu = 1;
+  p.bias = bias, p.residual = nullptr, p.out = reinterpret_cast<__nv_bfloat16*>(y);
+  L->block_n = 64, L->kblk = 32;
+  const char* base = reinterpret_cast<const char*>(padded);
+  const uint64_t row_bytes = (uint64_t)Wp * 8;
+  for (int py = 0; py < 2; ++py) {
+    int rc = encode_act_map(&p.tmA[py], base + py * row_bytes, 32, (uint64_t)Wo, (uint64_t)(Hp - py + 1) / 2, (uint64_t)N,
+                            16, 2 * row_bytes, (uint64_t)Hp * row_bytes, p.tw, p.th, 32);
+    if (rc) return rc;
+  }
+  for (int ky = 0; ky < 7; ++ky) p.tap_map[ky] = (int8_t)(ky & 1), p.tap_dh[ky] = (int16_t)(ky >> 1), p.tap_dw[ky] = 0;
+  int rc = encode_weight_map(&p.tmB, w224, 224, 64, 64, 32);
+  if (rc) return rc;
+  const int total = p.num_m_tiles;
+  const int sms = sm_count();
+  L->grid = total < sms ? total : sms;
   return 0;
 }
 
@@ -383,10 +430,11 @@ int conv_tc_prepare(const ConvGeom& g, const void* x, const void* w, const float
 
 int conv_tc_run(const ConvTcPrepared* prep, cudaStream_t stream) {
   const ConvTcLaunch* L = reinterpret_cast<const ConvTcLaunch*>(prep->storage);
+  if (L->kblk == 32) return launch_bn<64, 32>(*L, stream);
   switch (L->block_n) {
-    case 256: return launch_bn<256>(*L, stream);
-    case 128: return launch_bn<128>(*L, stream);
-    default: return launch_bn<64>(*L, stream);
+    case 256: return launch_bn<256, 64>(*L, stream);
+    case 128: return launch_bn<128, 64>(*L, stream);
+    default: return launch_bn<64, 64>(*L, stream);
   }
 }
 

@@ -3,7 +3,7 @@
 // [False, True, True]).  The plan owns the BN-folded bf16 weights; activations live in the caller's workspace:
 //   bufA / bufB : block input / output ping-pong (largest: layer4 output, 2048 ch at H/8 x W/8)
 //   t1 / t2     : bottleneck inner tensors
-// Layer list (55 convs): stem 7x7/2 (CUDA-core f32, fused normalise) -> maxpool -> 16 bottlenecks
+// Layer list (55 convs): stem 7x7/2 (normalise + pad staging pass, then tcgen05 implicit GEMM) -> maxpool -> 16 bottlenecks
 // (conv1 1x1 +ReLU, conv2 3x3 stride/dilation +ReLU, conv3 1x1 + residual + ReLU, optional downsample 1x1)
 // -> FCNHead conv3x3 + ReLU -> 1x1 (512 -> 3) + bias as f32 planar logits.
 #include <map>
@@ -44,6 +44,7 @@ struct nbc_plan {
   float mean[3], std[3];
   float* stem_w = nullptr;  // f32 [64][7][7][3]
   float* stem_b = nullptr;
+  __nv_bfloat16* stem_w224 = nullptr;  // bf16 [64][7][8][4] for the tensor-core stem
   std::vector<nbc::Block> blocks;
   nbc::ConvLayer head;
   float* cls_w = nullptr;  // f32 [3][512]
@@ -97,6 +98,8 @@ static void buffer_sizes(int N, int H, int W, size_t* big, size_t* small) {
   s = s > p8 * 512 ? s : p8 * 512;
   *big = align_up(b * N * 2, 1024);
   *small = align_up(s * N * 2, 1024);
+  const size_t stem_ws = nbc_stem_tc_workspace_bytes(N, H, W);   // the padded bf16 image lives in t2
+  if (*small < stem_ws) *small = stem_ws;
 }
 
 static int add_conv(nbc_plan* p, const ConvLayer& L, int N, int H, int W, const void* x, const void* residual, void* y,
@@ -137,7 +140,12 @@ static int build_steps(nbc_plan* p, int N, int H, int W, void* workspace) {
     memset(&s.prep, 0, sizeof(s.prep));
     s.kind = 0, s.g = ConvGeom{N, H, W, 3, 64, 7, 7, 2, 3, 1, 1}, s.x = images, s.y = bufB;
     s.name = "stem";
-    s.w = p->stem_w, s.bias = p->stem_b, s.residual = nullptr;
+    s.w = p->stem_w, s.bias = p->stem_b, s.residual = t2;   // residual slot = staging buffer of the padded image
+    if (p->impl != 2) {
+      s.kind = 5;  // tensor-core stem
+      int rc = conv_tc_prepare_stem(N, d.H2, d.W2, 2 * d.H2 + 5, 2 * d.W2 + 6, t2, p->stem_w224, p->stem_b, bufB, &s.prep);
+      if (rc) return rc;
+    }
     steps.push_back(s);
     Step m;
     memset(&m.prep, 0, sizeof(m.prep));
@@ -191,6 +199,11 @@ static int run_step(nbc_plan* p, const Step& s, const void* input, int input_kin
                             stream);
       return nbc_stem_u8(reinterpret_cast<const uint8_t*>(input), s.g.N, s.g.H, s.g.W, p->mean, p->std, p->stem_w,
                          p->stem_b, s.y, stream);
+    case 5: {
+      int rc = stem_tc_pad(input, input_kind, s.g.N, s.g.H, s.g.W, p->mean, p->std, const_cast<void*>(s.residual), stream);
+      if (rc) return rc;
+      return conv_tc_run(&s.prep, stream);
+    }
     case 1: return nbc_maxpool3x3s2_bf16(s.x, s.g.N, s.g.H, s.g.W, 64, s.y, stream);
     case 2: return conv_tc_run(&s.prep, stream);
     case 3: return conv_mma(s.g, s.x, s.w, s.bias, s.residual, s.y, stream);
@@ -254,6 +267,8 @@ extern "C" nbc_plan* nbc_plan_create(const void* const* t, int n_tensors, const 
     rc = fold_pack(reinterpret_cast<const float*>(t[0]), reinterpret_cast<const float*>(t[1]),
                    reinterpret_cast<const float*>(t[2]), reinterpret_cast<const float*>(t[3]),
                    reinterpret_cast<const float*>(t[4]), nullptr, 1e-5f, 64, 3, 7, 7, 3, nullptr, p->stem_w, p->stem_b, 0);
+  if (!rc) rc = dev_alloc(p, reinterpret_cast<void**>(&p->stem_w224), 64 * 224 * 2);
+  if (!rc) rc = nbc_stem_pack_weights(p->stem_w, p->stem_w224, 0);
   idx = 6;
   const int nblocks[4] = {3, 4, 6, 3};
   const int planes[4] = {64, 128, 256, 512};

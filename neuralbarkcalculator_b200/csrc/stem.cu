@@ -6,6 +6,7 @@
 // K = 7*7*3 = 147 is too ragged for a TMA/UMMA tile; this first version runs on CUDA cores in f32:
 // one CTA = 16x16 output pixels x 64 channels, input tile and all weights staged in shared memory.
 #include "common.cuh"
+#include "conv.h"
 
 namespace nbc {
 
@@ -94,6 +95,44 @@ __global__ void __launch_bounds__(256) stem_kernel(const StemParams p) {
   }
 }
 
+// ---- tensor-core stem: staging pass -----------------------------------------------------------------------------
+// Writes the normalised image as bf16 [N][Hp][Wp][4] (channel 3 = 0) with an explicit zero border of 3 pixels, so
+// that tap row ky of output (ho, wo) is the 64 contiguous bytes starting at padded pixel (2*ho + ky, 2*wo).
+// Hp = 2*Ho + 5, Wp = 2*Wo + 6.  The implicit GEMM itself is conv_tc_kernel<64, 32> (conv_tc.cu).
+template <bool kF32>
+__global__ void __launch_bounds__(256) stem_pad_kernel(const StemParams p, int Hp, int Wp, uint2* __restrict__ padded) {
+  const int64_t total = (int64_t)p.N * Hp * Wp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % Wp) - 3;
+    int64_t t = i / Wp;
+    const int y = (int)(t % Hp) - 3;
+    const int img = (int)(t / Hp);
+    float v[3] = {0.f, 0.f, 0.f};
+    if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
+      if (kF32) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) v[ch] = __ldg(p.xf + (((int64_t)img * 3 + ch) * p.H + y) * p.W + x);
+      } else {
+        const uint8_t* s = p.img + (((int64_t)img * p.H + y) * p.W + x) * 3;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+          v[ch] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)s[ch], 255.f), p.mean[ch]), p.std[ch]);
+      }
+    }
+    padded[i] = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], 0.f));
+  }
+}
+
+// stem weights f32 [64][7][7][3] (BN folded) -> bf16 [64][7][8][4], zero for kx == 7 or c == 3  (K = 224)
+__global__ void stem_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 224) return;
+  const int c = i & 3, kx = (i >> 2) & 7, ky = (i >> 5) % 7, oc = i / 224;
+  float v = 0.f;
+  if (c < 3 && kx < 7) v = w[((oc * 7 + ky) * 7 + kx) * 3 + c];
+  out[i] = __float2bfloat16_rn(v);
+}
+
 // maxpool 3x3 stride 2 pad 1 (padding = -inf), bf16 NHWC, 8 channels per thread
 __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C,
                                                       int Ho, int Wo, __nv_bfloat16* __restrict__ y) {
@@ -167,6 +206,62 @@ extern "C" int nbc_stem_f32(const float* x_nchw, int N, int H, int W, const floa
   NBC_REQUIRE(x_nchw, "nbc_stem_f32: null pointer");
   return stem_launch(nullptr, x_nchw, N, H, W, nullptr, nullptr, w_stem, bias, out,
                      reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t nbc_stem_tc_workspace_bytes(int N, int H, int W) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  return align_up((size_t)N * (2 * Ho + 5) * (2 * Wo + 6) * 8, 1024);
+}
+
+extern "C" int nbc_stem_pack_weights(const float* w_stem_f32, void* w224_bf16, void* stream) {
+  NBC_REQUIRE(w_stem_f32 && w224_bf16, "nbc_stem_pack_weights: null pointer");
+  stem_pack_kernel<<<ceil_div(64 * 224, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      w_stem_f32, reinterpret_cast<__nv_bfloat16*>(w224_bf16));
+  NBC_CHECK_LAUNCH();
+  return 0;
+}
+
+namespace nbc {
+int stem_tc_pad(const void* input, int input_kind, int N, int H, int W, const float* mean3, const float* std3, void* padded,
+                cudaStream_t stream) {
+  StemParams p;
+  memset(&p, 0, sizeof(p));
+  p.img = input_kind == 0 ? reinterpret_cast<const uint8_t*>(input) : nullptr;
+  p.xf = input_kind == 1 ? reinterpret_cast<const float*>(input) : nullptr;
+  p.N = N, p.H = H, p.W = W, p.Ho = (H - 1) / 2 + 1, p.Wo = (W - 1) / 2 + 1;
+  for (int i = 0; i < 3; ++i) p.mean[i] = mean3 ? mean3[i] : 0.f, p.std[i] = std3 ? std3[i] : 1.f;
+  const int Hp = 2 * p.Ho + 5, Wp = 2 * p.Wo + 6;
+  const int64_t total = (int64_t)N * Hp * Wp;
+  const int blocks = (int)(ceil_div64(total, 256) < 148 * 16 ? ceil_div64(total, 256) : 148 * 16);
+  if (input_kind == 1)
+    stem_pad_kernel<true><<<blocks, 256, 0, stream>>>(p, Hp, Wp, reinterpret_cast<uint2*>(padded));
+  else
+    stem_pad_kernel<false><<<blocks, 256, 0, stream>>>(p, Hp, Wp, reinterpret_cast<uint2*>(padded));
+  NBC_CHECK_LAUNCH();
+  return 0;
+}
+}  // namespace nbc
+
+extern "C" int nbc_stem_tc(const void* input, int input_kind, int N, int H, int W, const float* mean3_host,
+                           const float* std3_host, const void* w224_bf16, const float* bias, void* workspace,
+                           size_t workspace_bytes, void* out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  NBC_REQUIRE(input && w224_bf16 && bias && workspace && out, "nbc_stem_tc: null pointer");
+  NBC_REQUIRE(input_kind == 0 || input_kind == 1, "nbc_stem_tc: input_kind must be 0 (u8 NHWC) or 1 (f32 NCHW)");
+  NBC_REQUIRE(input_kind == 1 || (mean3_host && std3_host), "nbc_stem_tc: mean/std required for u8 input");
+  NBC_REQUIRE(N > 0 && H > 0 && W > 0, "nbc_stem_tc: bad shape");
+  NBC_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 16 == 0, "nbc_stem_tc: workspace must be 16-byte aligned");
+  if (workspace_bytes < nbc_stem_tc_workspace_bytes(N, H, W)) {
+    set_error("nbc_stem_tc: workspace too small");
+    return NBC_ERR_WORKSPACE;
+  }
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  int rc = stem_tc_pad(input, input_kind, N, H, W, mean3_host, std3_host, workspace, stream);
+  if (rc) return rc;
+  ConvTcPrepared prep;
+  rc = conv_tc_prepare_stem(N, Ho, Wo, 2 * Ho + 5, 2 * Wo + 6, workspace, w224_bf16, bias, out, &prep);
+  if (rc) return rc;
+  return conv_tc_run(&prep, stream);
 }
 
 extern "C" int nbc_maxpool3x3s2_bf16(const void* x, int N, int H, int W, int C, void* y, void* stream_) {

@@ -130,6 +130,30 @@ def stem_f32(x, w_stem, bias):
     return out
 
 
+def stem_tc(inp, mean, std, w_stem, bias):
+    """Tensor-core stem: inp u8 NHWC or f32 NCHW; w_stem f32 [64,7,7,3] (BN folded) -> bf16 NHWC [N,H/2,W/2,64]."""
+    lib = _lib.load()
+    _dev(inp, 'input')
+    inp = inp.contiguous()
+    if inp.dtype == torch.uint8:
+        N, H, W, _ = inp.shape
+        kind = 0
+    else:
+        N, _, H, W = inp.shape
+        kind = 1
+    m3 = (C.c_float * 3)(*mean)
+    s3 = (C.c_float * 3)(*std)
+    with torch.cuda.device(inp.device):
+        w224 = torch.empty(64 * 224, dtype=torch.bfloat16, device=inp.device)
+        _lib.check(lib.nbc_stem_pack_weights(_ptr(_contig(w_stem, torch.float32, 'w_stem')), _ptr(w224), _stream(inp.device)),
+                   'nbc_stem_pack_weights')
+        ws = torch.empty(lib.nbc_stem_tc_workspace_bytes(N, H, W), dtype=torch.uint8, device=inp.device)
+        out = torch.empty((N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64), dtype=torch.bfloat16, device=inp.device)
+        _lib.check(lib.nbc_stem_tc(_ptr(inp), kind, N, H, W, m3, s3, _ptr(w224), _ptr(_contig(bias, torch.float32, 'bias')),
+                                   _ptr(ws), ws.numel(), _ptr(out), _stream(inp.device)), 'nbc_stem_tc')
+    return out
+
+
 def maxpool3x3s2(x):
     lib = _lib.load()
     x = _contig(x, torch.bfloat16, 'x')

@@ -180,6 +180,19 @@ def test_stem_maxpool_head(cuda_device):
     assert (got - ref).abs().max() < 2.0 ** -8 * ref.abs().max() + 1e-3
     y2 = ops.stem_f32(x.to(dev), wf, bf)
     assert torch.equal(y2, y)
+    # tensor-core stem (bf16 operands): same conv within bf16 operand rounding, u8 and f32 inputs bit-identical,
+    # odd sizes and a batch
+    for inp in (torch.from_numpy(img).unsqueeze(0).to(dev), x.to(dev)):
+        yt = ops.stem_tc(inp, omodel.DEFAULT_MEAN, omodel.DEFAULT_STD, wf, bf)
+        gt = yt.float().cpu().permute(0, 3, 1, 2)
+        assert gt.shape == ref.shape
+        assert (gt - ref).abs().max() < 0.02 * ref.abs().max() + 1e-2, (gt - ref).abs().max()
+    big = np.stack([synth.texture_u8(203, 517, 5), synth.texture_u8(203, 517, 6)])
+    yb = ops.stem_tc(torch.from_numpy(big).to(dev), omodel.DEFAULT_MEAN, omodel.DEFAULT_STD, wf, bf).float().cpu()
+    for i in range(2):
+        r = torch.nn.functional.conv2d(omodel.normalise_u8(big[i]), w * scale.view(-1, 1, 1, 1), bn[1] - bn[2] * scale,
+                                       stride=2, padding=3).relu()
+        assert (yb[i].permute(2, 0, 1) - r[0]).abs().max() < 0.02 * r.abs().max() + 1e-2
     p = ops.maxpool3x3s2(y)
     refp = torch.nn.functional.max_pool2d(y.float().cpu().permute(0, 3, 1, 2), 3, 2, 1)
     assert torch.equal(p.float().cpu().permute(0, 3, 1, 2), refp)
