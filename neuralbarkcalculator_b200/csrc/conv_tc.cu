@@ -13,7 +13,8 @@
 //   * both land in 128B-swizzled K-major smem and are consumed by tcgen05.mma (M=128, N=BLOCK_N, K=16) issued
 //     by one thread; the f32 accumulator lives in TMEM, double buffered so the epilogue of tile i overlaps the
 //     main loop of tile i+1.
-//   * epilogue (4 warps): tcgen05.ld -> + bias (+ residual) -> ReLU -> bf16 -> 64 B vector stores.
+//   * epilogue (4 warps): tcgen05.ld -> smem transpose -> + bias (+ residual) -> ReLU -> bf16 -> coalesced 16 B
+//     stores (8 pixels x 64 contiguous bytes per instruction).
 // Persistent CTAs (one per SM), warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue.
 #include "common.cuh"
 #include "conv.h"
@@ -47,9 +48,10 @@ struct TcCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int kSmemBytes = (kStages * kStageBytes + 1024 /*barriers*/ + 1024 /*alignment slack*/) < 120 * 1024
-                                        ? 120 * 1024  /* > half an SM: keeps one CTA (one TMEM owner) per SM */
-                                        : (kStages * kStageBytes + 2048);
+  static constexpr int kStagingBytes = 4 * 32 * 36 * 4;  // epilogue transpose tiles: 4 warps x 32 rows x 36 words
+  static constexpr int kUsedBytes = kStages * kStageBytes + 1024 /*barriers*/ + kStagingBytes + 1024 /*align slack*/;
+  // > half an SM's shared memory keeps one CTA (one TMEM owner) per SM
+  static constexpr int kSmemBytes = kUsedBytes < 120 * 1024 ? 120 * 1024 : kUsedBytes;
   static constexpr uint32_t kSwizzleBytes = KBLK * 2;  // 128 or 64
 };
 
@@ -155,9 +157,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     __syncwarp();
   } else {
     // ================================ epilogue (warps 2..5) ================================
+    // TMEM gives each thread one pixel row of the accumulator; storing that directly would touch 32 different
+    // pixels per instruction (half-used sectors).  Each warp therefore transposes 32-column chunks through a private
+    // padded smem tile (pitch 36 words: conflict-free for 16-byte accesses both ways) and does the bias / residual /
+    // ReLU / bf16 pack in the "coalesced domain": 4 lanes cover 64 contiguous bytes of one pixel, 8 pixels per
+    // instruction, for the residual loads and the output stores alike.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    const int hl = row >> p.tw_log2, wl = row & (p.tw - 1);
+    float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 1024) + q * (32 * 36);
+    const int crow = lane >> 2, cpiece = lane & 3;
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.num_n_tiles;
@@ -166,9 +173,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       m_tile /= p.tiles_w;
       const int th_i = m_tile % p.tiles_h;
       const int img = m_tile / p.tiles_h;
-      const int w = (tw_i << p.tw_log2) + wl, h = th_i * p.th + hl, n0 = n_tile * BN;
-      const bool valid = (w < p.Wo) && (h < p.Ho);
-      const int64_t off = (((int64_t)img * p.Ho + h) * p.Wo + w) * p.Cout + n0;
+      const int n0 = n_tile * BN;
+      int64_t offs[4];
+      bool ok[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int row = q * 32 + crow + 8 * j;
+        const int w = (tw_i << p.tw_log2) + (row & (p.tw - 1)), h = th_i * p.th + (row >> p.tw_log2);
+        ok[j] = (w < p.Wo) && (h < p.Ho);
+        offs[j] = (((int64_t)img * p.Ho + h) * p.Wo + w) * p.Cout + n0 + cpiece * 8;
+      }
       mbar_wait(&tfull_bar[acc], acc_phase, 400 + (int)acc);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -177,41 +191,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         uint32_t r[32];
         tmem_ld32(t_row + c, r);
         uint4 res[4];
-        const bool has_res = (p.residual != nullptr) && valid;
-        if (has_res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c);
+        if (p.residual != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) res[i] = __ldg(rp + i);
+          for (int j = 0; j < 4; ++j)
+            if (ok[j]) res[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + offs[j] + c));
         }
-        float bv[32];
-        const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b4 = __ldg(bp + i);
-          bv[4 * i] = b4.x, bv[4 * i + 1] = b4.y, bv[4 * i + 2] = b4.z, bv[4 * i + 3] = b4.w;
-        }
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + cpiece * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + cpiece * 8 + 4));
         tmem_ld_wait();
-        uint32_t o[16];
+        float4* wr = reinterpret_cast<float4*>(stg + lane * 36);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float v0 = __uint_as_float(r[2 * i]) + bv[2 * i];
-          float v1 = __uint_as_float(r[2 * i + 1]) + bv[2 * i + 1];
-          if (has_res) {
-            const uint32_t rv = reinterpret_cast<const uint32_t*>(res)[i];
-            v0 += bf16lo(rv);
-            v1 += bf16hi(rv);
-          }
-          if (p.relu) {
-            v0 = fmaxf(v0, 0.f);
-            v1 = fmaxf(v1, 0.f);
-          }
-          o[i] = pack_bf16x2(v0, v1);
-        }
-        if (valid) {
-          uint4* op = reinterpret_cast<uint4*>(p.out + off + c);
+        for (int i = 0; i < 8; ++i)
+          wr[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                              __uint_as_float(r[4 * i + 3]));
+        __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 4; ++i) op[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        for (int j = 0; j < 4; ++j) {
+          const float4* rd = reinterpret_cast<const float4*>(stg + (crow + 8 * j) * 36 + cpiece * 8);
+          const float4 v0 = rd[0], v1 = rd[1];
+          float v[8] = {v0.x + b0.x, v0.y + b0.y, v0.z + b0.z, v0.w + b0.w, v1.x + b1.x, v1.y + b1.y, v1.z + b1.z, v1.w + b1.w};
+          if (ok[j]) {
+            if (p.residual != nullptr) {
+              const uint32_t rv[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) v[2 * k] += bf16lo(rv[k]), v[2 * k + 1] += bf16hi(rv[k]);
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+            }
+            *reinterpret_cast<uint4*>(p.out + offs[j] + c) =
+                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();

@@ -10,6 +10,9 @@
 
 namespace nbc {
 
+// kIters = Cin / 256: every lane owns 8 consecutive channels of each 256-channel slab and keeps its 3 x 8 x kIters
+// weights in registers, so the inner loop is one 16-byte load + 24 FMAs per slab.
+template <int kIters>
 __global__ void __launch_bounds__(256) head1x1_kernel(const __nv_bfloat16* __restrict__ x, int64_t P, int N, int Cin,
                                                       const float* __restrict__ w, const float* __restrict__ bias,
                                                       float* __restrict__ logits) {
@@ -18,19 +21,28 @@ __global__ void __launch_bounds__(256) head1x1_kernel(const __nv_bfloat16* __res
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t M = (int64_t)N * P;
   const float b0 = __ldg(bias), b1 = __ldg(bias + 1), b2 = __ldg(bias + 2);
+  float wr[kIters][3][8];
+#pragma unroll
+  for (int it = 0; it < kIters; ++it)
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) wr[it][k][e] = __ldg(w + k * Cin + it * 256 + lane * 8 + e);
   for (int64_t m = warp_global; m < M; m += nwarps) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    const __nv_bfloat16* xr = x + m * Cin;
-    for (int c = lane * 8; c < Cin; c += 256) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(xr + c));
-      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    const __nv_bfloat16* xr = x + m * Cin + lane * 8;
+    uint4 v[kIters];
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) v[it] = __ldg(reinterpret_cast<const uint4*>(xr + it * 256));
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const uint32_t u[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float f0 = bf16lo(u[k]), f1 = bf16hi(u[k]);
-        const int ci = c + 2 * k;
-        a0 = fmaf(f0, __ldg(w + ci), a0), a0 = fmaf(f1, __ldg(w + ci + 1), a0);
-        a1 = fmaf(f0, __ldg(w + Cin + ci), a1), a1 = fmaf(f1, __ldg(w + Cin + ci + 1), a1);
-        a2 = fmaf(f0, __ldg(w + 2 * Cin + ci), a2), a2 = fmaf(f1, __ldg(w + 2 * Cin + ci + 1), a2);
+        a0 = fmaf(f0, wr[it][0][2 * k], a0), a0 = fmaf(f1, wr[it][0][2 * k + 1], a0);
+        a1 = fmaf(f0, wr[it][1][2 * k], a1), a1 = fmaf(f1, wr[it][1][2 * k + 1], a1);
+        a2 = fmaf(f0, wr[it][2][2 * k], a2), a2 = fmaf(f1, wr[it][2][2 * k + 1], a2);
       }
     }
 #pragma unroll
@@ -124,12 +136,18 @@ extern "C" int nbc_head_1x1(const void* x_bf16, int64_t pixels_per_image, int N,
                             const float* bias3, float* logits_planar, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   NBC_REQUIRE(x_bf16 && w3xC && bias3 && logits_planar, "nbc_head_1x1: null pointer");
-  NBC_REQUIRE(Cin % 8 == 0 && N > 0 && pixels_per_image > 0, "nbc_head_1x1: bad shape");
+  NBC_REQUIRE((Cin == 256 || Cin == 512 || Cin == 1024) && N > 0 && pixels_per_image > 0,
+              "nbc_head_1x1: Cin must be 256, 512 or 1024 (got %d)", Cin);
   const int64_t M = (int64_t)N * pixels_per_image;
-  const int64_t want = ceil_div64(M, 8);
-  const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
-  head1x1_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x_bf16), pixels_per_image, N, Cin,
-                                             w3xC, bias3, logits_planar);
+  const int64_t want = ceil_div64(M, 8 * 4);
+  const int blocks = (int)(want < 148 * 8 ? (want < 1 ? 1 : want) : 148 * 8);
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x_bf16);
+  if (Cin == 256)
+    head1x1_kernel<1><<<blocks, 256, 0, stream>>>(xb, pixels_per_image, N, Cin, w3xC, bias3, logits_planar);
+  else if (Cin == 512)
+    head1x1_kernel<2><<<blocks, 256, 0, stream>>>(xb, pixels_per_image, N, Cin, w3xC, bias3, logits_planar);
+  else
+    head1x1_kernel<4><<<blocks, 256, 0, stream>>>(xb, pixels_per_image, N, Cin, w3xC, bias3, logits_planar);
   NBC_CHECK_LAUNCH();
   return 0;
 }
