@@ -13,9 +13,9 @@
 //   * both land in 128B-swizzled K-major smem and are consumed by tcgen05.mma (M=128, N=BLOCK_N, K=16) issued
 //     by one thread; the f32 accumulator lives in TMEM, double buffered so the epilogue of tile i overlaps the
 //     main loop of tile i+1.
-//   * epilogue (4 warps): tcgen05.ld -> smem transpose -> + bias (+ residual) -> ReLU -> bf16 -> coalesced 16 B
-//     stores (8 pixels x 64 contiguous bytes per instruction).
-// Persistent CTAs (one per SM), warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue.
+//   * epilogue (8 warps): tcgen05.ld -> smem transpose -> + bias (+ residual, prefetched) -> ReLU -> bf16 ->
+//     coalesced 16 B stores.
+// Persistent CTAs (one per SM), warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..9 = epilogue.
 #include "common.cuh"
 #include "conv.h"
 
@@ -37,7 +37,7 @@ struct ConvTcParams {
   int16_t tap_dw[9];
 };
 
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 // BN = output channels per tile, KBLK = K elements per pipeline stage: 64 (128-byte swizzle) for the bottleneck /
 // head convs, 32 (64-byte swizzle) for the stem, whose K block is one 7-tap row of 8 pixels x 4 channels.
@@ -48,7 +48,7 @@ struct TcCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int kStagingBytes = 4 * 32 * 36 * 4;  // epilogue transpose tiles: 4 warps x 32 rows x 36 words
+  static constexpr int kStagingBytes = 8 * 32 * 20 * 4;  // epilogue transpose tiles: 8 warps x 32 rows x 20 words
   static constexpr int kUsedBytes = kStages * kStageBytes + 1024 /*barriers*/ + kStagingBytes + 1024 /*align slack*/;
   // > half an SM's shared memory keeps one CTA (one TMEM owner) per SM
   static constexpr int kSmemBytes = kUsedBytes < 120 * 1024 ? 120 * 1024 : kUsedBytes;
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 8);
     }
     fence_mbar_init();
   }
@@ -156,15 +156,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     }
     __syncwarp();
   } else {
-    // ================================ epilogue (warps 2..5) ================================
+    // ================================ epilogue (warps 2..9) ================================
     // TMEM gives each thread one pixel row of the accumulator; storing that directly would touch 32 different
-    // pixels per instruction (half-used sectors).  Each warp therefore transposes 32-column chunks through a private
-    // padded smem tile (pitch 36 words: conflict-free for 16-byte accesses both ways) and does the bias / residual /
-    // ReLU / bf16 pack in the "coalesced domain": 4 lanes cover 64 contiguous bytes of one pixel, 8 pixels per
-    // instruction, for the residual loads and the output stores alike.
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 1024) + q * (32 * 36);
-    const int crow = lane >> 2, cpiece = lane & 3;
+    // pixels per instruction.  Each warp therefore transposes 16-column chunks through a private padded smem tile
+    // (pitch 20 words: conflict-free for 16-byte accesses both ways) and does bias / residual / ReLU / bf16 pack in
+    // the "coalesced domain": 2 lanes cover the 32 contiguous bytes a pixel owns in the chunk, 16 pixels per
+    // instruction, for the residual loads and the output stores alike.  Eight warps (two per TMEM lane quarter, each
+    // owning half of the tile's columns) and residual loads issued one chunk ahead keep enough bytes in flight to
+    // hide the L2 / HBM latency on the low-K layers, where this epilogue -- not the MMA -- sets the pace.
+    const int ew = warp - 2;
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = ew >> 2;        // which half of the BN columns
+    constexpr int kCols = BN / 2;    // columns per warp
+    float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 1024) + ew * (32 * 20);
+    const int crow = lane >> 1, cpiece = lane & 1;
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.num_n_tiles;
@@ -173,45 +178,53 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       m_tile /= p.tiles_w;
       const int th_i = m_tile % p.tiles_h;
       const int img = m_tile / p.tiles_h;
-      const int n0 = n_tile * BN;
-      int64_t offs[4];
-      bool ok[4];
+      const int n0 = n_tile * BN + half * kCols;
+      int64_t offs[2];
+      bool ok[2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int row = q * 32 + crow + 8 * j;
+      for (int j = 0; j < 2; ++j) {
+        const int row = q * 32 + crow + 16 * j;
         const int w = (tw_i << p.tw_log2) + (row & (p.tw - 1)), h = th_i * p.th + (row >> p.tw_log2);
         ok[j] = (w < p.Wo) && (h < p.Ho);
         offs[j] = (((int64_t)img * p.Ho + h) * p.Wo + w) * p.Cout + n0 + cpiece * 8;
       }
+      const bool has_res = p.residual != nullptr;
+      uint4 res_nxt[2];
+      if (has_res) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          if (ok[j]) res_nxt[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + offs[j]));
+      }
       mbar_wait(&tfull_bar[acc], acc_phase, 400 + (int)acc);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(t_row + c, r);
-        uint4 res[4];
-        if (p.residual != nullptr) {
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * kCols;
+#pragma unroll 2
+      for (int c = 0; c < kCols; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(t_row + c, r);
+        uint4 res[2];
+        res[0] = res_nxt[0], res[1] = res_nxt[1];
+        if (has_res && c + 16 < kCols) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (ok[j]) res[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + offs[j] + c));
+          for (int j = 0; j < 2; ++j)
+            if (ok[j]) res_nxt[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + offs[j] + c + 16));
         }
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + cpiece * 8));
         const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + cpiece * 8 + 4));
         tmem_ld_wait();
-        float4* wr = reinterpret_cast<float4*>(stg + lane * 36);
+        float4* wr = reinterpret_cast<float4*>(stg + lane * 20);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 4; ++i)
           wr[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
                               __uint_as_float(r[4 * i + 3]));
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4* rd = reinterpret_cast<const float4*>(stg + (crow + 8 * j) * 36 + cpiece * 8);
+        for (int j = 0; j < 2; ++j) {
+          const float4* rd = reinterpret_cast<const float4*>(stg + (crow + 16 * j) * 20 + cpiece * 8);
           const float4 v0 = rd[0], v1 = rd[1];
           float v[8] = {v0.x + b0.x, v0.y + b0.y, v0.z + b0.z, v0.w + b0.w, v1.x + b1.x, v1.y + b1.y, v1.z + b1.z, v1.w + b1.w};
           if (ok[j]) {
-            if (p.residual != nullptr) {
+            if (has_res) {
               const uint32_t rv[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
 #pragma unroll
               for (int k = 0; k < 4; ++k) v[2 * k] += bf16lo(rv[k]), v[2 * k + 1] += bf16hi(rv[k]);
