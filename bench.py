@@ -242,7 +242,7 @@ def main():
             def step_host():
                 res['rows'], res['counts'], _ = eng.run_host(host, masks_host, bgr=True, bottom_up=True, exclude_nodes=True)
             ms_h, _ = timed(step_host, args.steps, max(1, args.warmup))
-            d2h = int(sum(r * 1024 for r in res['rows']) + B * 12 + B * 8)
+            d2h = int(B * 1024 * 1024 + B * 12 + B * 8)     # mask canvases + counts + {first,last}
             e2e = {'value': world * B * args.steps / (ms_h / 1000.0), 'unit': 'images/s',
                    'h2d_bytes_per_step': B * RAW * RAW * 3, 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_h / args.steps}
 

@@ -103,12 +103,24 @@ int nbc_head_1x1(const void* x_bf16, int64_t pixels_per_image, int N, int Cin, c
 int nbc_upsample_argmax(const float* logits, int N, int h, int w, int H, int W, uint8_t* mask, void* stream);
 int nbc_upsample_bicubic(const float* logits, int N, int C, int h, int w, int H, int W, float* out, void* stream);
 
+/* ragged batch variant: mask canvas u8 [N,Hc,W], image n has heights[n] valid rows (device array); its logits
+ * occupy ceil(heights[n]/8) rows of the [N,3,hc,w] logits canvas.  Rows beyond the valid height are not written. */
+int nbc_upsample_argmax_ragged(const float* logits, int N, int hc, int w, int Hc, int W, const int32_t* heights,
+                               uint8_t* mask, void* stream);
+/* heights[n] = last - first from the {first,last}[N] pairs written by nbc_preprocess_4x_u8 (device -> device) */
+int nbc_heights_from_first_last(const int32_t* first_last, int N, int32_t* heights, void* stream);
+
 /* ---- K5: small-region removal + class counts  (utils.py:135-148, models.py:273-276, 323-332) ------------------
  * mask u8 [N,H,W] in place; 8-connected; regions with size < threshold are flipped (two-stage).
  * exclude_nodes != 0 rewrites class 2 -> 1 afterwards.  counts: int32 [N,3] pixels per class of the result. */
 size_t nbc_ccl_workspace_bytes(int N, int H, int W);
 int nbc_remove_small_zones(uint8_t* mask, int N, int H, int W, int threshold, int exclude_nodes, int32_t* counts,
                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ragged batch variant: only rows [0, heights[n]) of image n take part (labelling, flips and counts) */
+int nbc_remove_small_zones_ragged(uint8_t* mask, int N, int Hc, int W, const int32_t* heights, int threshold,
+                                  int exclude_nodes, int32_t* counts, void* workspace, size_t workspace_bytes,
+                                  void* stream);
 
 /* ---- K4: max-of-class-index weighted cross entropy, forward + backward  (utils.py:151-165) ----------------------
  * logits f32 [N,3,H,W]; target u8 [N,H,W] (target_is_i64: int64); weights f32[3].  loss: f32 scalar (mean over
@@ -129,6 +141,14 @@ size_t nbc_plan_workspace_bytes(const nbc_plan* plan, int N, int H, int W);
  * input_kind 1: f32 NCHW [N,3,H,W] already normalised.  -> lowres_logits f32 [N,3,ceil(H/8),ceil(W/8)] */
 int nbc_plan_forward(nbc_plan* plan, const void* input, int input_kind, int N, int H, int W, float* lowres_logits,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* Ragged batch: N images of different heights in one canvas u8 [N,Hc,W,3]; image n occupies rows [0, height_n).
+ * Heights are read ON THE DEVICE -- either heights[N] or the {first,last}[N] pairs written by nbc_preprocess_4x_u8
+ * (exactly one of the two non-NULL) -- so a whole batch is enqueued without a host round trip.  Every layer treats
+ * rows >= its per-image valid height as the conv zero padding (tiles beyond are skipped), which makes each image's
+ * logits bit-identical to running it alone.  lowres_logits: f32 [N,3,ceil(Hc/8),ceil(W/8)], valid rows only. */
+int nbc_plan_forward_ragged(nbc_plan* plan, const uint8_t* canvas, int N, int Hc, int W, const int32_t* heights,
+                            const int32_t* first_last, float* lowres_logits, void* workspace,
+                            size_t workspace_bytes, void* stream);
 /* per-layer timing of the last shape (debug / profiling): runs the forward with events around every layer;
  * ms_out[n_layers] and flops_out[n_layers] (may be NULL); returns number of layers or <0 */
 int nbc_plan_profile(nbc_plan* plan, const void* input, int input_kind, int N, int H, int W, float* lowres_logits,

@@ -34,14 +34,20 @@ SIGNATURES = {
     'nbc_head_1x1': (c_int, [c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'nbc_upsample_argmax': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'nbc_upsample_bicubic': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'nbc_upsample_argmax_ragged': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'nbc_heights_from_first_last': (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     'nbc_ccl_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'nbc_remove_small_zones': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'nbc_remove_small_zones_ragged': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t,
+                                      c_void_p]),
     'nbc_wce_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'nbc_wce_fwd_bwd': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'nbc_plan_create': (c_void_p, [C.POINTER(c_void_p), c_int, C.POINTER(c_float), C.POINTER(c_float)]),
     'nbc_plan_destroy': (None, [c_void_p]),
     'nbc_plan_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int]),
     'nbc_plan_forward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'nbc_plan_forward_ragged': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                c_void_p]),
     'nbc_plan_profile': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p,
                                  C.POINTER(c_float), C.POINTER(C.c_double), c_int]),
     'nbc_plan_set_impl': (c_int, [c_void_p, c_int]),

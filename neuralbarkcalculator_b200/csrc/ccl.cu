@@ -15,12 +15,20 @@ namespace nbc {
 
 // src[p] != 0 <=> pixel p belongs to the set being labelled.  Labels are indices into the whole [N,H,W] buffer
 // and always satisfy labels[p] <= p, -1 for pixels outside the set.
-__global__ void __launch_bounds__(256) ccl_init(const uint8_t* __restrict__ src, int W, int64_t total,
-                                                int* __restrict__ labels, int* __restrict__ sizes) {
+// vh (optional): ragged batch, image n has vh[n] valid rows of the H-row canvas; pixels below are outside the image
+__device__ __forceinline__ bool row_valid(int64_t p, int H, int W, const int* vh) {
+  if (vh == nullptr) return true;
+  const int64_t r = p / W;
+  return (int)(r % H) < __ldg(vh + (int)(r / H));
+}
+
+__global__ void __launch_bounds__(256) ccl_init(const uint8_t* __restrict__ src, int H, int W, int64_t total,
+                                                int* __restrict__ labels, int* __restrict__ sizes,
+                                                const int* __restrict__ vh) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const bool inb = p < total;
-  const bool in = inb && src[p] != 0;
+  const bool in = inb && row_valid(p, H, W, vh) && src[p] != 0;
   const int x = inb ? (int)(p % W) : 0;
   const unsigned m = __ballot_sync(0xffffffffu, in);
   const unsigned rowstart = __ballot_sync(0xffffffffu, x == 0);
@@ -65,7 +73,7 @@ __device__ __forceinline__ void unite(int* labels, int a, int b) {
 __global__ void __launch_bounds__(256) ccl_merge(const uint8_t* __restrict__ src, int H, int W, int64_t total,
                                                  int* __restrict__ labels) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= total || src[p] == 0) return;
+  if (p >= total || labels[p] < 0) return;   // labels < 0: not in the set (or outside a ragged image)
   const int lane = threadIdx.x & 31;
   const int x = (int)(p % W);
   const int y = (int)((p / W) % H);
@@ -105,9 +113,14 @@ __global__ void __launch_bounds__(256) ccl_flatten_count(int64_t total, int thre
 // stage A result: setB[p] = background after removing small foreground components
 __global__ void __launch_bounds__(256) ccl_stage_a_apply(const uint8_t* __restrict__ mask, const int* __restrict__ labels,
                                                          const int* __restrict__ sizes, int threshold, int64_t total,
-                                                         uint8_t* __restrict__ setB) {
+                                                         uint8_t* __restrict__ setB, int H, int W,
+                                                         const int* __restrict__ vh) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= total) return;
+  if (!row_valid(p, H, W, vh)) {
+    setB[p] = 0;
+    return;
+  }
   const bool bg = (mask[p] == 0) || (__ldcg(sizes + labels[p]) < threshold);
   setB[p] = bg ? 1 : 0;
 }
@@ -115,14 +128,14 @@ __global__ void __launch_bounds__(256) ccl_stage_a_apply(const uint8_t* __restri
 __global__ void __launch_bounds__(256) ccl_final(uint8_t* __restrict__ mask, const uint8_t* __restrict__ setB,
                                                  const int* __restrict__ labels, const int* __restrict__ sizes,
                                                  int threshold, int exclude_nodes, int64_t HW,
-                                                 int* __restrict__ counts) {
+                                                 int* __restrict__ counts, int W, const int* __restrict__ vh) {
   __shared__ int s_cnt[3];
   if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   const int n = blockIdx.y;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int cls = -1;
-  if (i < HW) {
+  if (i < HW && (vh == nullptr || (int)(i / W) < __ldg(vh + n))) {
     const int64_t p = (int64_t)n * HW + i;
     const uint8_t m = mask[p];
     const bool bg = setB[p] && (__ldcg(sizes + labels[p]) >= threshold);
@@ -149,9 +162,8 @@ extern "C" size_t nbc_ccl_workspace_bytes(int N, int H, int W) {
   return align_up(total * 4, 256) * 2 + align_up(total, 256);
 }
 
-extern "C" int nbc_remove_small_zones(uint8_t* mask, int N, int H, int W, int threshold, int exclude_nodes,
-                                      int32_t* counts, void* workspace, size_t workspace_bytes, void* stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+static int remove_small_zones_impl(uint8_t* mask, int N, int H, int W, int threshold, int exclude_nodes, int32_t* counts,
+                                   void* workspace, size_t workspace_bytes, const int* vh, cudaStream_t stream) {
   NBC_REQUIRE(mask && counts && workspace, "nbc_remove_small_zones: null pointer");
   NBC_REQUIRE(N > 0 && H > 0 && W > 0 && N <= 65535, "nbc_remove_small_zones: bad shape");
   const int64_t total = (int64_t)N * H * W;
@@ -167,16 +179,16 @@ extern "C" int nbc_remove_small_zones(uint8_t* mask, int N, int H, int W, int th
   const unsigned blocks = (unsigned)ceil_div64(total, 256);
   NBC_CUDA(cudaMemsetAsync(counts, 0, (size_t)N * 3 * sizeof(int32_t), stream));
   // stage A: foreground components
-  ccl_init<<<blocks, 256, 0, stream>>>(mask, W, total, labels, sizes);
+  ccl_init<<<blocks, 256, 0, stream>>>(mask, H, W, total, labels, sizes, vh);
   NBC_CHECK_LAUNCH();
   ccl_merge<<<blocks, 256, 0, stream>>>(mask, H, W, total, labels);
   NBC_CHECK_LAUNCH();
   ccl_flatten_count<<<blocks, 256, 0, stream>>>(total, threshold, labels, sizes);
   NBC_CHECK_LAUNCH();
-  ccl_stage_a_apply<<<blocks, 256, 0, stream>>>(mask, labels, sizes, threshold, total, setB);
+  ccl_stage_a_apply<<<blocks, 256, 0, stream>>>(mask, labels, sizes, threshold, total, setB, H, W, vh);
   NBC_CHECK_LAUNCH();
   // stage B: background components of the stage-A result
-  ccl_init<<<blocks, 256, 0, stream>>>(setB, W, total, labels, sizes);
+  ccl_init<<<blocks, 256, 0, stream>>>(setB, H, W, total, labels, sizes, nullptr);
   NBC_CHECK_LAUNCH();
   ccl_merge<<<blocks, 256, 0, stream>>>(setB, H, W, total, labels);
   NBC_CHECK_LAUNCH();
@@ -184,7 +196,21 @@ extern "C" int nbc_remove_small_zones(uint8_t* mask, int N, int H, int W, int th
   NBC_CHECK_LAUNCH();
   const int64_t HW = (int64_t)H * W;
   dim3 grid((unsigned)ceil_div64(HW, 256), N);
-  ccl_final<<<grid, 256, 0, stream>>>(mask, setB, labels, sizes, threshold, exclude_nodes, HW, counts);
+  ccl_final<<<grid, 256, 0, stream>>>(mask, setB, labels, sizes, threshold, exclude_nodes, HW, counts, W, vh);
   NBC_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int nbc_remove_small_zones(uint8_t* mask, int N, int H, int W, int threshold, int exclude_nodes,
+                                      int32_t* counts, void* workspace, size_t workspace_bytes, void* stream) {
+  return remove_small_zones_impl(mask, N, H, W, threshold, exclude_nodes, counts, workspace, workspace_bytes, nullptr,
+                                 reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nbc_remove_small_zones_ragged(uint8_t* mask, int N, int Hc, int W, const int32_t* heights, int threshold,
+                                             int exclude_nodes, int32_t* counts, void* workspace, size_t workspace_bytes,
+                                             void* stream) {
+  NBC_REQUIRE(heights, "nbc_remove_small_zones_ragged: null heights");
+  return remove_small_zones_impl(mask, N, Hc, W, threshold, exclude_nodes, counts, workspace, workspace_bytes, heights,
+                                 reinterpret_cast<cudaStream_t>(stream));
 }

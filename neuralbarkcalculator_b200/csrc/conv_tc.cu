@@ -32,11 +32,15 @@ struct ConvTcParams {
   int num_m_tiles, num_n_tiles;
   int n_taps, cblocks;
   int relu;
+  // ragged batches: valid_h[img] = number of valid OUTPUT rows of image img (nullptr: all rows valid).  Rows at or
+  // beyond it are written as zeros for kRaggedHalo rows (the zero padding the next layer reads) and skipped after.
+  const int* valid_h;
   int8_t tap_map[9];
   int16_t tap_dh[9];
   int16_t tap_dw[9];
 };
 
+constexpr int kRaggedHalo = 4;   // >= the largest padding / dilation of any consumer (layer4: dilation 4)
 constexpr int kTcThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 // BN = output channels per tile, KBLK = K elements per pipeline stage: 64 (128-byte swizzle) for the bottleneck /
@@ -106,6 +110,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         const int th_i = m_tile % p.tiles_h;
         const int img = m_tile / p.tiles_h;
         const int w0 = tw_i << p.tw_log2, h0 = th_i * p.th, n0 = n_tile * BN;
+        if (p.valid_h != nullptr && h0 >= __ldg(p.valid_h + img)) continue;  // dead tile of a ragged batch
         for (int tap = 0; tap < p.n_taps; ++tap) {
           const CUtensorMap* mA = &p.tmA[p.tap_map[tap]];
           const int cw = w0 + p.tap_dw[tap], ch = h0 + p.tap_dh[tap];
@@ -130,6 +135,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        if (p.valid_h != nullptr) {
+          const int mt = tile / p.num_n_tiles / p.tiles_w;
+          if ((mt % p.tiles_h) * p.th >= __ldg(p.valid_h + mt / p.tiles_h)) continue;
+        }
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 300 + (int)acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -180,20 +189,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       const int img = m_tile / p.tiles_h;
       const int n0 = n_tile * BN + half * kCols;
       int64_t offs[2];
-      bool ok[2];
+      bool ok[2];     // this row is stored
+      bool live[2];   // ... with computed values (otherwise zeros: the halo rows of a ragged batch)
+      const int vh = p.valid_h != nullptr ? __ldg(p.valid_h + img) : INT_MAX;
+      const int vz = p.valid_h != nullptr ? vh + kRaggedHalo : INT_MAX;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int row = q * 32 + crow + 16 * j;
         const int w = (tw_i << p.tw_log2) + (row & (p.tw - 1)), h = th_i * p.th + (row >> p.tw_log2);
-        ok[j] = (w < p.Wo) && (h < p.Ho);
+        ok[j] = (w < p.Wo) && (h < p.Ho) && (h < vz);
+        live[j] = h < vh;
         offs[j] = (((int64_t)img * p.Ho + h) * p.Wo + w) * p.Cout + n0 + cpiece * 8;
+      }
+      if (th_i * p.th >= vh) {
+        // dead tile: no MMA was issued for it; only the zero halo is written
+        if (th_i * p.th < vz) {
+          for (int c = 0; c < kCols; c += 16)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              if (ok[j]) *reinterpret_cast<uint4*>(p.out + offs[j] + c) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        continue;
       }
       const bool has_res = p.residual != nullptr;
       uint4 res_nxt[2];
       if (has_res) {
 #pragma unroll
         for (int j = 0; j < 2; ++j)
-          if (ok[j]) res_nxt[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + offs[j]));
+          if (ok[j] && live[j]) res_nxt[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + offs[j]));
       }
       mbar_wait(&tfull_bar[acc], acc_phase, 400 + (int)acc);
       tc_fence_after();
@@ -207,7 +230,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         if (has_res && c + 16 < kCols) {
 #pragma unroll
           for (int j = 0; j < 2; ++j)
-            if (ok[j]) res_nxt[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + offs[j] + c + 16));
+            if (ok[j] && live[j]) res_nxt[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + offs[j] + c + 16));
         }
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + cpiece * 8));
         const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + cpiece * 8 + 4));
@@ -224,7 +247,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           const float4 v0 = rd[0], v1 = rd[1];
           float v[8] = {v0.x + b0.x, v0.y + b0.y, v0.z + b0.z, v0.w + b0.w, v1.x + b1.x, v1.y + b1.y, v1.z + b1.z, v1.w + b1.w};
           if (ok[j]) {
-            if (has_res) {
+            if (has_res && live[j]) {
               const uint32_t rv[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
 #pragma unroll
               for (int k = 0; k < 4; ++k) v[2 * k] += bf16lo(rv[k]), v[2 * k + 1] += bf16hi(rv[k]);
@@ -234,7 +257,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
               for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
             }
             *reinterpret_cast<uint4*>(p.out + offs[j] + c) =
-                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                live[j] ? make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                     pack_bf16x2(v[6], v[7]))
+                        : make_uint4(0u, 0u, 0u, 0u);
           }
         }
         __syncwarp();
@@ -416,7 +441,7 @@ static int launch_bn(const ConvTcLaunch& L, cudaStream_t stream) {
 // The windows of neighbouring outputs overlap (stride 16 B, extent 64 B): the tensor map simply describes that
 // address function.  Even / odd padded rows are two lattices, exactly like the stride-2 convolutions.
 int conv_tc_prepare_stem(int N, int Ho, int Wo, int Hp, int Wp, const void* padded, const void* w224, const float* bias,
-                         void* y, ConvTcPrepared* out) {
+                         void* y, ConvTcPrepared* out, const int* valid_h) {
   ConvTcLaunch* L = reinterpret_cast<ConvTcLaunch*>(out->storage);
   ConvTcParams& p = L->p;
   memset(&p, 0, sizeof(p));
@@ -426,6 +451,7 @@ int conv_tc_prepare_stem(int N, int Ho, int Wo, int Hp, int Wp, const void* padd
   p.num_n_tiles = 1;
   p.n_taps = 7, p.cblocks = 1, p.relu = 1;
   p.bias = bias, p.residual = nullptr, p.out = reinterpret_cast<__nv_bfloat16*>(y);
+  p.valid_h = valid_h;
   L->block_n = 64, L->kblk = 32;
   const char* base = reinterpret_cast<const char*>(padded);
   const uint64_t row_bytes = (uint64_t)Wp * 8;
@@ -444,14 +470,16 @@ int conv_tc_prepare_stem(int N, int Ho, int Wo, int Hp, int Wp, const void* padd
 }
 
 int conv_tc_prepare(const ConvGeom& g, const void* x, const void* w, const float* bias, const void* residual, void* y,
-                    ConvTcPrepared* out) {
+                    ConvTcPrepared* out, const int* valid_h) {
   static_assert(sizeof(ConvTcLaunch) <= sizeof(out->storage), "ConvTcPrepared::storage too small");
   if (!conv_tc_supported(g)) {
     set_error("conv_tc: unsupported shape Cin=%d Cout=%d k=%dx%d stride=%d", g.Cin, g.Cout, g.kh, g.kw, g.stride);
     return NBC_ERR_INVALID;
   }
   ConvTcLaunch* L = reinterpret_cast<ConvTcLaunch*>(out->storage);
-  return build_launch(g, x, w, bias, residual, y, L);
+  int rc = build_launch(g, x, w, bias, residual, y, L);
+  L->p.valid_h = valid_h;
+  return rc;
 }
 
 int conv_tc_run(const ConvTcPrepared* prep, cudaStream_t stream) {

@@ -128,9 +128,59 @@ __global__ void __launch_bounds__(256) upsample_kernel(const float* __restrict__
   }
 }
 
+// Ragged batch: image n has H_n valid rows in a canvas of Hc rows; its logits occupy ceil(H_n/8) rows of the hc-row
+// logits canvas.  Same arithmetic as upsample_kernel<true> with per-image in/out heights (scale = h_n / H_n).
+__global__ void __launch_bounds__(256) upsample_argmax_ragged_kernel(const float* __restrict__ logits, int hc, int w, int Hc,
+                                                                     int W, float scale_x, const int* __restrict__ heights,
+                                                                     uint8_t* __restrict__ mask) {
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Y = blockIdx.y;
+  const int n = blockIdx.z;
+  const int H = min(max(__ldg(heights + n), 1), Hc);
+  if (X >= W || Y >= H) return;
+  const int h = ((((H - 1) / 2 + 1) - 1) / 2 + 1 - 1) / 2 + 1;
+  const float scale_y = __fdiv_rn((float)h, (float)H);
+  int ix[4], iy[4];
+  float wx[4], wy[4];
+  cubic_taps(X, scale_x, w, ix, wx);
+  cubic_taps(Y, scale_y, h, iy, wy);
+  const int64_t plane = (int64_t)hc * w;
+  float best = 0.f;
+  int arg = 0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = cubic_sample(logits + ((int64_t)n * 3 + c) * plane, w, iy, wy, ix, wx);
+    if (c == 0 || v > best) best = v, arg = c;
+  }
+  mask[((int64_t)n * Hc + Y) * W + X] = (uint8_t)arg;
+}
+
+__global__ void heights_kernel(const int* __restrict__ first_last, int N, int* __restrict__ heights) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < N) heights[n] = first_last[2 * n + 1] - first_last[2 * n];
+}
+
 }  // namespace nbc
 
 using namespace nbc;
+
+extern "C" int nbc_heights_from_first_last(const int32_t* first_last, int N, int32_t* heights, void* stream) {
+  NBC_REQUIRE(first_last && heights && N > 0, "nbc_heights_from_first_last: bad argument");
+  heights_kernel<<<ceil_div(N, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(first_last, N, heights);
+  NBC_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int nbc_upsample_argmax_ragged(const float* logits, int N, int hc, int w, int Hc, int W, const int32_t* heights,
+                                          uint8_t* mask, void* stream) {
+  NBC_REQUIRE(logits && heights && mask, "nbc_upsample_argmax_ragged: null pointer");
+  NBC_REQUIRE(N > 0 && hc > 0 && w > 0 && Hc > 0 && W > 0 && Hc <= 65535 && N <= 65535, "nbc_upsample_argmax_ragged: bad shape");
+  dim3 grid(ceil_div(W, 256), Hc, N);
+  upsample_argmax_ragged_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, hc, w, Hc, W,
+                                                                                           (float)w / (float)W, heights, mask);
+  NBC_CHECK_LAUNCH();
+  return 0;
+}
 
 extern "C" int nbc_head_1x1(const void* x_bf16, int64_t pixels_per_image, int N, int Cin, const float* w3xC,
                             const float* bias3, float* logits_planar, void* stream_) {

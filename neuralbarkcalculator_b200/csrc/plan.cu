@@ -52,7 +52,7 @@ struct nbc_plan {
   std::vector<void*> allocs;
   int impl = 0;
   // cached launch lists (tensor maps are encoded once per shape / workspace): key = (N, H, W, workspace, impl)
-  typedef std::tuple<int, int, int, void*, int> Key;
+  typedef std::tuple<int, int, int, void*, int, int> Key;   // N, H, W, workspace, impl, ragged
   std::map<Key, std::vector<nbc::Step>> cache;
   std::vector<nbc::Step>* steps_ptr = nullptr;
 };
@@ -102,16 +102,27 @@ static void buffer_sizes(int N, int H, int W, size_t* big, size_t* small) {
   if (*small < stem_ws) *small = stem_ws;
 }
 
+// levels: device int[4][N] of a ragged batch (nullptr for a dense batch); *level = resolution level of the input
+// (0 full, 1 half, 2 quarter, 3 eighth), advanced by stride-2 layers
 static int add_conv(nbc_plan* p, const ConvLayer& L, int N, int H, int W, const void* x, const void* residual, void* y,
-                    const char* name, int* Ho, int* Wo) {
+                    const char* name, int* Ho, int* Wo, const int* levels = nullptr, int* level = nullptr) {
   Step s;
   memset(&s.prep, 0, sizeof(s.prep));
   s.g = ConvGeom{N, H, W, L.Cin, L.Cout, L.k, L.k, L.stride, L.pad, L.dil, L.relu};
   s.x = x, s.w = L.w, s.bias = L.bias, s.residual = residual, s.y = y, s.name = name;
   const bool tc = (p->impl != 2) && conv_tc_supported(s.g);
   s.kind = tc ? 2 : 3;
+  const int* vh = nullptr;
+  if (levels != nullptr) {
+    if (!tc) {
+      set_error("plan: ragged batches need the tcgen05 path (layer %s)", name);
+      return NBC_ERR_INVALID;
+    }
+    if (L.stride == 2) ++*level;
+    vh = levels + (size_t)(*level) * N;
+  }
   if (tc) {
-    int rc = conv_tc_prepare(s.g, x, L.w, L.bias, residual, y, &s.prep);
+    int rc = conv_tc_prepare(s.g, x, L.w, L.bias, residual, y, &s.prep, vh);
     if (rc) return rc;
   } else if (!conv_mma_supported(s.g)) {
     set_error("plan: layer %s has no kernel (Cin=%d Cout=%d)", name, L.Cin, L.Cout);
@@ -122,7 +133,7 @@ static int add_conv(nbc_plan* p, const ConvLayer& L, int N, int H, int W, const 
   return 0;
 }
 
-static int build_steps(nbc_plan* p, int N, int H, int W, void* workspace) {
+static int build_steps(nbc_plan* p, int N, int H, int W, void* workspace, bool ragged) {
   std::vector<Step>& steps = *p->steps_ptr;
   steps.clear();
   const void* images = nullptr;   // the stem input and the logits output are patched in at run time
@@ -134,6 +145,7 @@ static int build_steps(nbc_plan* p, int N, int H, int W, void* workspace) {
   void* bufB = ws + big;
   void* t1 = ws + 2 * big;
   void* t2 = ws + 2 * big + small;
+  const int* levels = ragged ? reinterpret_cast<const int*>(ws + 2 * big + 2 * small) : nullptr;
   const Dims d = dims_of(H, W);
   {
     Step s;
@@ -141,37 +153,46 @@ static int build_steps(nbc_plan* p, int N, int H, int W, void* workspace) {
     s.kind = 0, s.g = ConvGeom{N, H, W, 3, 64, 7, 7, 2, 3, 1, 1}, s.x = images, s.y = bufB;
     s.name = "stem";
     s.w = p->stem_w, s.bias = p->stem_b, s.residual = t2;   // residual slot = staging buffer of the padded image
+    if (ragged && p->impl == 2) {
+      set_error("plan: ragged batches need the tcgen05 path");
+      return NBC_ERR_INVALID;
+    }
     if (p->impl != 2) {
       s.kind = 5;  // tensor-core stem
-      int rc = conv_tc_prepare_stem(N, d.H2, d.W2, 2 * d.H2 + 5, 2 * d.W2 + 6, t2, p->stem_w224, p->stem_b, bufB, &s.prep);
+      int rc = conv_tc_prepare_stem(N, d.H2, d.W2, 2 * d.H2 + 5, 2 * d.W2 + 6, t2, p->stem_w224, p->stem_b, bufB, &s.prep,
+                                    ragged ? levels + N : nullptr);
       if (rc) return rc;
     }
+    s.w = levels;   // w slot of the stem / maxpool steps = ragged level table (or nullptr)
     steps.push_back(s);
     Step m;
     memset(&m.prep, 0, sizeof(m.prep));
     m.kind = 1, m.g = ConvGeom{N, d.H2, d.W2, 64, 64, 3, 3, 2, 1, 1, 0}, m.x = bufB, m.y = bufA, m.name = "maxpool";
-    m.w = nullptr, m.bias = nullptr, m.residual = nullptr;
+    m.w = levels, m.bias = nullptr, m.residual = nullptr;
     steps.push_back(m);
   }
   int h = d.H4, w = d.W4;
+  int level = 2;   // the bottlenecks start at quarter resolution
   void* in = bufA;
   void* other = bufB;
   for (size_t b = 0; b < p->blocks.size(); ++b) {
     const Block& B = p->blocks[b];
     int h1, w1, h2, w2, h3, w3;
-    int rc = add_conv(p, B.c1, N, h, w, in, nullptr, t1, "conv1", &h1, &w1);
+    int lv_in = level, lv = level;
+    int rc = add_conv(p, B.c1, N, h, w, in, nullptr, t1, "conv1", &h1, &w1, levels, &lv);
     if (rc) return rc;
-    rc = add_conv(p, B.c2, N, h1, w1, t1, nullptr, t2, "conv2", &h2, &w2);
+    rc = add_conv(p, B.c2, N, h1, w1, t1, nullptr, t2, "conv2", &h2, &w2, levels, &lv);
     if (rc) return rc;
+    level = lv;
     if (B.has_ds) {
       int hd, wd;
-      rc = add_conv(p, B.ds, N, h, w, in, nullptr, other, "downsample", &hd, &wd);
+      rc = add_conv(p, B.ds, N, h, w, in, nullptr, other, "downsample", &hd, &wd, levels, &lv_in);
       if (rc) return rc;
       // the block input is dead after conv1 and downsample: conv3 overwrites it, residual = downsample output
-      rc = add_conv(p, B.c3, N, h2, w2, t2, other, in, "conv3", &h3, &w3);
+      rc = add_conv(p, B.c3, N, h2, w2, t2, other, in, "conv3", &h3, &w3, levels, &lv);
       if (rc) return rc;
     } else {
-      rc = add_conv(p, B.c3, N, h2, w2, t2, in, other, "conv3", &h3, &w3);
+      rc = add_conv(p, B.c3, N, h2, w2, t2, in, other, "conv3", &h3, &w3, levels, &lv);
       if (rc) return rc;
       void* tmp = in;
       in = other;
@@ -180,7 +201,7 @@ static int build_steps(nbc_plan* p, int N, int H, int W, void* workspace) {
     h = h3, w = w3;
   }
   int hh, wh;
-  int rc = add_conv(p, p->head, N, h, w, in, nullptr, t1, "head3x3", &hh, &wh);
+  int rc = add_conv(p, p->head, N, h, w, in, nullptr, t1, "head3x3", &hh, &wh, levels, &level);
   if (rc) return rc;
   Step s;
   memset(&s.prep, 0, sizeof(s.prep));
@@ -200,11 +221,15 @@ static int run_step(nbc_plan* p, const Step& s, const void* input, int input_kin
       return nbc_stem_u8(reinterpret_cast<const uint8_t*>(input), s.g.N, s.g.H, s.g.W, p->mean, p->std, p->stem_w,
                          p->stem_b, s.y, stream);
     case 5: {
-      int rc = stem_tc_pad(input, input_kind, s.g.N, s.g.H, s.g.W, p->mean, p->std, const_cast<void*>(s.residual), stream);
+      int rc = stem_tc_pad(input, input_kind, s.g.N, s.g.H, s.g.W, p->mean, p->std, const_cast<void*>(s.residual), stream,
+                           reinterpret_cast<const int*>(s.w));
       if (rc) return rc;
       return conv_tc_run(&s.prep, stream);
     }
-    case 1: return nbc_maxpool3x3s2_bf16(s.x, s.g.N, s.g.H, s.g.W, 64, s.y, stream);
+    case 1:
+      if (s.w != nullptr)
+        return maxpool_ragged(s.x, s.g.N, s.g.H, s.g.W, 64, s.y, reinterpret_cast<const int*>(s.w) + 2 * (size_t)s.g.N, stream);
+      return nbc_maxpool3x3s2_bf16(s.x, s.g.N, s.g.H, s.g.W, 64, s.y, stream);
     case 2: return conv_tc_run(&s.prep, stream);
     case 3: return conv_mma(s.g, s.x, s.w, s.bias, s.residual, s.y, stream);
     case 4:
@@ -214,7 +239,7 @@ static int run_step(nbc_plan* p, const Step& s, const void* input, int input_kin
 }
 
 static int ensure_steps(nbc_plan* p, const void* images, int input_kind, int N, int H, int W, float* logits,
-                        void* workspace, size_t workspace_bytes) {
+                        void* workspace, size_t workspace_bytes, bool ragged = false) {
   NBC_REQUIRE(p && images && logits && workspace, "nbc_plan_forward: null pointer");
   NBC_REQUIRE(N > 0 && H >= 16 && W >= 16, "nbc_plan_forward: bad shape %dx%dx%d", N, H, W);
   NBC_REQUIRE(input_kind == 0 || input_kind == 1, "nbc_plan_forward: input_kind must be 0 (u8 NHWC) or 1 (f32 NCHW)");
@@ -224,7 +249,7 @@ static int ensure_steps(nbc_plan* p, const void* images, int input_kind, int N, 
   }
   NBC_REQUIRE(reinterpret_cast<uintptr_t>(workspace) % 1024 == 0, "nbc_plan_forward: workspace must be 1024-byte aligned");
   (void)images, (void)logits;
-  nbc_plan::Key key(N, H, W, workspace, p->impl);
+  nbc_plan::Key key(N, H, W, workspace, p->impl, ragged ? 1 : 0);
   auto it = p->cache.find(key);
   if (it != p->cache.end()) {
     p->steps_ptr = &it->second;
@@ -232,7 +257,7 @@ static int ensure_steps(nbc_plan* p, const void* images, int input_kind, int N, 
   }
   if (p->cache.size() >= 256) p->cache.clear();
   p->steps_ptr = &p->cache[key];
-  int rc = build_steps(p, N, H, W, workspace);
+  int rc = build_steps(p, N, H, W, workspace, ragged);
   if (rc) {
     p->cache.erase(key);
     p->steps_ptr = nullptr;
@@ -332,7 +357,7 @@ extern "C" void nbc_plan_destroy(nbc_plan* p) {
 extern "C" size_t nbc_plan_workspace_bytes(const nbc_plan*, int N, int H, int W) {
   size_t big, small;
   buffer_sizes(N, H, W, &big, &small);
-  return 2 * big + 2 * small;
+  return 2 * big + 2 * small + align_up((size_t)4 * N * sizeof(int), 1024);   // + ragged level table
 }
 
 extern "C" int nbc_plan_set_impl(nbc_plan* p, int impl) {
@@ -348,6 +373,26 @@ extern "C" int nbc_plan_forward(nbc_plan* p, const void* input, int input_kind, 
   if (rc) return rc;
   for (const Step& s : *p->steps_ptr) {
     rc = run_step(p, s, input, input_kind, lowres_logits, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" int nbc_plan_forward_ragged(nbc_plan* p, const uint8_t* canvas, int N, int Hc, int W, const int32_t* heights,
+                                       const int32_t* first_last, float* lowres_logits, void* workspace,
+                                       size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  NBC_REQUIRE((heights != nullptr) != (first_last != nullptr),
+              "nbc_plan_forward_ragged: give exactly one of heights / first_last");
+  int rc = ensure_steps(p, canvas, 0, N, Hc, W, lowres_logits, workspace, workspace_bytes, true);
+  if (rc) return rc;
+  size_t big, small;
+  buffer_sizes(N, Hc, W, &big, &small);
+  int* levels = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + 2 * big + 2 * small);
+  rc = ragged_levels(heights, first_last, N, Hc, levels, stream);
+  if (rc) return rc;
+  for (const Step& s : *p->steps_ptr) {
+    rc = run_step(p, s, canvas, 0, lowres_logits, stream);
     if (rc) return rc;
   }
   return 0;

@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(256) stem_kernel(const StemParams p) {
 // that tap row ky of output (ho, wo) is the 64 contiguous bytes starting at padded pixel (2*ho + ky, 2*wo).
 // Hp = 2*Ho + 5, Wp = 2*Wo + 6.  The implicit GEMM itself is conv_tc_kernel<64, 32> (conv_tc.cu).
 template <bool kF32>
-__global__ void __launch_bounds__(256) stem_pad_kernel(const StemParams p, int Hp, int Wp, uint2* __restrict__ padded) {
+__global__ void __launch_bounds__(256) stem_pad_kernel(const StemParams p, int Hp, int Wp, uint2* __restrict__ padded,
+                                                       const int* __restrict__ valid_h) {
   const int64_t total = (int64_t)p.N * Hp * Wp;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int x = (int)(i % Wp) - 3;
@@ -108,7 +109,8 @@ __global__ void __launch_bounds__(256) stem_pad_kernel(const StemParams p, int H
     const int y = (int)(t % Hp) - 3;
     const int img = (int)(t / Hp);
     float v[3] = {0.f, 0.f, 0.f};
-    if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
+    const int vh = valid_h ? min(p.H, __ldg(valid_h + img)) : p.H;   // ragged batch: rows >= vh are zero padding
+    if (y >= 0 && y < vh && x >= 0 && x < p.W) {
       if (kF32) {
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) v[ch] = __ldg(p.xf + (((int64_t)img * 3 + ch) * p.H + y) * p.W + x);
@@ -135,7 +137,8 @@ __global__ void stem_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __r
 
 // maxpool 3x3 stride 2 pad 1 (padding = -inf), bf16 NHWC, 8 channels per thread
 __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C,
-                                                      int Ho, int Wo, __nv_bfloat16* __restrict__ y) {
+                                                      int Ho, int Wo, __nv_bfloat16* __restrict__ y,
+                                                      const int* __restrict__ valid_h) {
   const int cg = C >> 3;
   const int64_t total = (int64_t)N * Ho * Wo * cg;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -145,6 +148,13 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __res
     t /= Wo;
     const int ho = (int)(t % Ho);
     const int n = (int)(t / Ho);
+    if (valid_h != nullptr) {   // ragged batch: zero halo rows after the valid ones, nothing beyond
+      const int vh = __ldg(valid_h + n);
+      if (ho >= vh) {
+        if (ho < vh + 4) *reinterpret_cast<uint4*>(y + (((int64_t)n * Ho + ho) * Wo + wo) * C + c8 * 8) = make_uint4(0, 0, 0, 0);
+        continue;
+      }
+    }
     __nv_bfloat162 m[4];
     const __nv_bfloat162 ninf = __floats2bfloat162_rn(-INFINITY, -INFINITY);
 #pragma unroll
@@ -223,7 +233,7 @@ extern "C" int nbc_stem_pack_weights(const float* w_stem_f32, void* w224_bf16, v
 
 namespace nbc {
 int stem_tc_pad(const void* input, int input_kind, int N, int H, int W, const float* mean3, const float* std3, void* padded,
-                cudaStream_t stream) {
+                cudaStream_t stream, const int* valid_h) {
   StemParams p;
   memset(&p, 0, sizeof(p));
   p.img = input_kind == 0 ? reinterpret_cast<const uint8_t*>(input) : nullptr;
@@ -234,9 +244,9 @@ int stem_tc_pad(const void* input, int input_kind, int N, int H, int W, const fl
   const int64_t total = (int64_t)N * Hp * Wp;
   const int blocks = (int)(ceil_div64(total, 256) < 148 * 16 ? ceil_div64(total, 256) : 148 * 16);
   if (input_kind == 1)
-    stem_pad_kernel<true><<<blocks, 256, 0, stream>>>(p, Hp, Wp, reinterpret_cast<uint2*>(padded));
+    stem_pad_kernel<true><<<blocks, 256, 0, stream>>>(p, Hp, Wp, reinterpret_cast<uint2*>(padded), valid_h);
   else
-    stem_pad_kernel<false><<<blocks, 256, 0, stream>>>(p, Hp, Wp, reinterpret_cast<uint2*>(padded));
+    stem_pad_kernel<false><<<blocks, 256, 0, stream>>>(p, Hp, Wp, reinterpret_cast<uint2*>(padded), valid_h);
   NBC_CHECK_LAUNCH();
   return 0;
 }
@@ -256,7 +266,7 @@ extern "C" int nbc_stem_tc(const void* input, int input_kind, int N, int H, int 
     return NBC_ERR_WORKSPACE;
   }
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  int rc = stem_tc_pad(input, input_kind, N, H, W, mean3_host, std3_host, workspace, stream);
+  int rc = stem_tc_pad(input, input_kind, N, H, W, mean3_host, std3_host, workspace, stream, nullptr);
   if (rc) return rc;
   ConvTcPrepared prep;
   rc = conv_tc_prepare_stem(N, Ho, Wo, 2 * Ho + 5, 2 * Wo + 6, workspace, w224_bf16, bias, out, &prep);
@@ -272,7 +282,41 @@ extern "C" int nbc_maxpool3x3s2_bf16(const void* x, int N, int H, int W, int C, 
   const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
   const int blocks = (int)(ceil_div64(total, 256) < 148 * 16 ? ceil_div64(total, 256) : 148 * 16);
   maxpool_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, Ho, Wo,
-                                             reinterpret_cast<__nv_bfloat16*>(y));
+                                             reinterpret_cast<__nv_bfloat16*>(y), nullptr);
   NBC_CHECK_LAUNCH();
   return 0;
 }
+
+namespace nbc {
+int maxpool_ragged(const void* x, int N, int H, int W, int C, void* y, const int* valid_h, cudaStream_t stream) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
+  const int blocks = (int)(ceil_div64(total, 256) < 148 * 16 ? ceil_div64(total, 256) : 148 * 16);
+  maxpool_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, Ho, Wo,
+                                             reinterpret_cast<__nv_bfloat16*>(y), valid_h);
+  NBC_CHECK_LAUNCH();
+  return 0;
+}
+
+// per-image valid rows at the four resolution levels of the network: levels[0..3][N] = H, H/2, H/4, H/8 (ceil chain);
+// heights come either as an int[N] array or as the {first,last} pairs K1 writes (first_last != nullptr)
+__global__ void ragged_levels_kernel(const int* __restrict__ heights, const int* __restrict__ first_last, int N, int Hc,
+                                     int* __restrict__ levels) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  int h = first_last ? first_last[2 * n + 1] - first_last[2 * n] : heights[n];
+  h = max(1, min(h, Hc));
+  levels[n] = h;
+  h = (h - 1) / 2 + 1;
+  levels[N + n] = h;
+  h = (h - 1) / 2 + 1;
+  levels[2 * N + n] = h;
+  h = (h - 1) / 2 + 1;
+  levels[3 * N + n] = h;
+}
+int ragged_levels(const int* heights, const int* first_last, int N, int Hc, int* levels, cudaStream_t stream) {
+  ragged_levels_kernel<<<ceil_div(N, 128), 128, 0, stream>>>(heights, first_last, N, Hc, levels);
+  NBC_CHECK_LAUNCH();
+  return 0;
+}
+}  // namespace nbc

@@ -205,6 +205,34 @@ def upsample_bicubic(logits, size):
     return out
 
 
+def upsample_argmax_ragged(logits, heights, canvas_hw, out=None):
+    """Ragged batch: logits f32 [N,3,hc,w] canvas, heights int32 [N] (CUDA) -> u8 mask canvas [N,Hc,W]; image n gets
+    rows [0, heights[n]) from its ceil(heights[n]/8) logit rows."""
+    lib = _lib.load()
+    logits = _contig(logits, torch.float32, 'logits')
+    heights = _contig(heights, torch.int32, 'heights')
+    N, Cc, hc, w = logits.shape
+    Hc, W = canvas_hw
+    with torch.cuda.device(logits.device):
+        if out is None:
+            out = torch.zeros((N, Hc, W), dtype=torch.uint8, device=logits.device)
+        _lib.check(lib.nbc_upsample_argmax_ragged(_ptr(logits), N, hc, w, Hc, W, _ptr(heights), _ptr(out),
+                                                  _stream(logits.device)), 'nbc_upsample_argmax_ragged')
+    return out
+
+
+def heights_from_first_last(first_last, out=None):
+    lib = _lib.load()
+    first_last = _contig(first_last, torch.int32, 'first_last')
+    N = first_last.shape[0]
+    with torch.cuda.device(first_last.device):
+        if out is None:
+            out = torch.empty(N, dtype=torch.int32, device=first_last.device)
+        _lib.check(lib.nbc_heights_from_first_last(_ptr(first_last), N, _ptr(out), _stream(first_last.device)),
+                   'nbc_heights_from_first_last')
+    return out
+
+
 # ---- K5 -------------------------------------------------------------------------------------------------------
 def remove_small_zones_u8(mask, threshold=150, exclude_nodes=False, workspace=None):
     """mask u8 CUDA [N,H,W], modified in place.  Returns (mask, counts int32 [N,3]).  (utils.py:135-148)"""
@@ -221,6 +249,26 @@ def remove_small_zones_u8(mask, threshold=150, exclude_nodes=False, workspace=No
         _lib.check(lib.nbc_remove_small_zones(_ptr(mask), N, H, W, int(threshold), 1 if exclude_nodes else 0, _ptr(counts),
                                               _ptr(workspace), workspace.numel(), _stream(mask.device)),
                    'nbc_remove_small_zones')
+    return mask, counts
+
+
+def remove_small_zones_ragged(mask, heights, threshold=150, exclude_nodes=False, workspace=None, counts=None):
+    """Ragged batch: mask u8 canvas [N,Hc,W] in place, only rows [0, heights[n]) of image n take part."""
+    lib = _lib.load()
+    _dev(mask, 'mask')
+    heights = _contig(heights, torch.int32, 'heights')
+    if mask.dtype != torch.uint8 or not mask.is_contiguous() or mask.dim() != 3:
+        raise RuntimeError('remove_small_zones_ragged expects a contiguous u8 [N,Hc,W] tensor')
+    N, H, W = mask.shape
+    with torch.cuda.device(mask.device):
+        need = lib.nbc_ccl_workspace_bytes(N, H, W)
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty(need, dtype=torch.uint8, device=mask.device)
+        if counts is None:
+            counts = torch.empty((N, 3), dtype=torch.int32, device=mask.device)
+        _lib.check(lib.nbc_remove_small_zones_ragged(_ptr(mask), N, H, W, _ptr(heights), int(threshold),
+                                                     1 if exclude_nodes else 0, _ptr(counts), _ptr(workspace),
+                                                     workspace.numel(), _stream(mask.device)), 'nbc_remove_small_zones_ragged')
     return mask, counts
 
 
@@ -313,6 +361,28 @@ class Plan:
             ws_ptr, ws_bytes = self._workspace(N, H, W)
             _lib.check(self._lib.nbc_plan_forward(C.c_void_p(self.handle), _ptr(inp), kind, N, H, W, _ptr(out),
                                                   C.c_void_p(ws_ptr), ws_bytes, _stream(self.device)), 'nbc_plan_forward')
+        return out
+
+    def forward_ragged(self, canvas, heights=None, first_last=None, out=None):
+        """canvas u8 [N,Hc,W,3]; image n occupies rows [0, h_n) with h_n = heights[n] or last-first of first_last[n]
+        (int32 CUDA tensors, read on the device).  Returns the f32 logits canvas [N,3,ceil(Hc/8),ceil(W/8)]."""
+        canvas = _contig(canvas, torch.uint8, 'canvas')
+        N, H, W, c = canvas.shape
+        if c != 3 or (heights is None) == (first_last is None):
+            raise RuntimeError('forward_ragged: u8 [N,Hc,W,3] canvas and exactly one of heights / first_last')
+        if heights is not None:
+            heights = _contig(heights, torch.int32, 'heights')
+        else:
+            first_last = _contig(first_last, torch.int32, 'first_last')
+        h = ((((H - 1) // 2 + 1) - 1) // 2 + 1 - 1) // 2 + 1
+        w = ((((W - 1) // 2 + 1) - 1) // 2 + 1 - 1) // 2 + 1
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.zeros((N, 3, h, w), dtype=torch.float32, device=self.device)
+            ws_ptr, ws_bytes = self._workspace(N, H, W)
+            _lib.check(self._lib.nbc_plan_forward_ragged(C.c_void_p(self.handle), _ptr(canvas), N, H, W, _ptr(heights),
+                                                         _ptr(first_last), _ptr(out), C.c_void_p(ws_ptr), ws_bytes,
+                                                         _stream(self.device)), 'nbc_plan_forward_ragged')
         return out
 
     def profile(self, inp):

@@ -106,6 +106,66 @@ def test_batch_equals_single(cuda_device, synthetic_sd):
         assert torch.equal(single[0], batched[i])
 
 
+def test_ragged_batch_is_bit_identical_to_single_images(cuda_device, synthetic_sd):
+    """Images of different heights in one canvas: logits, masks, region removal and counts equal the per-image runs."""
+    from neuralbarkcalculator_b200 import ops
+    m = _model(synthetic_sd, cuda_device)
+    plan = m.native_plan()
+    heights = [203, 336, 129, 64]
+    Hc, W = 336, 256
+    imgs = [synth.texture_u8(h, W, 50 + i) for i, h in enumerate(heights)]
+    canvas = np.random.default_rng(0).integers(0, 256, (len(heights), Hc, W, 3), dtype=np.uint8)   # garbage below
+    for i, im in enumerate(imgs):
+        canvas[i, :heights[i]] = im
+    hd = torch.tensor(heights, dtype=torch.int32, device=cuda_device)
+    cv = torch.from_numpy(canvas).to(cuda_device)
+    low = plan.forward_ragged(cv, heights=hd)
+    fl = torch.tensor([[7, 7 + h] for h in heights], dtype=torch.int32, device=cuda_device)
+    low2 = plan.forward_ragged(cv, first_last=fl)
+    mask = ops.upsample_argmax_ragged(low, hd, (Hc, W))
+    mask_cc, counts = ops.remove_small_zones_ragged(mask.clone(), hd, 150, exclude_nodes=True)
+    for i, h in enumerate(heights):
+        t = torch.from_numpy(imgs[i]).unsqueeze(0).to(cuda_device)
+        single = m.lowres_logits_u8(t)
+        hl = single.shape[2]
+        assert torch.equal(low[i, :, :hl], single[0]), 'ragged logits differ for image %d' % i
+        assert torch.equal(low2[i, :, :hl], single[0])
+        smask = ops.upsample_argmax(single, (h, W))
+        assert torch.equal(mask[i, :h], smask[0])
+        sm, sc = ops.remove_small_zones_u8(smask.clone(), 150, exclude_nodes=True)
+        assert torch.equal(mask_cc[i, :h], sm[0])
+        assert torch.equal(counts[i], sc[0])
+
+
+def test_engine_matches_per_image_path(cuda_device, synthetic_sd):
+    """PredictEngine (ragged chunks, multi-stream) == per-image K1 -> predict_array, from device and from host buffers."""
+    import neuralbarkcalculator_b200 as nbc
+    from neuralbarkcalculator_b200 import engine, ops
+    calc = nbc.NeuralBarkCalculator(None, 'cuda:0', state_dict=synthetic_sd)
+    raws = []
+    for i, (top, bottom) in enumerate(((801, 1199), (400, 403), (1200, 400))):
+        img, _, _ = synth.raw_image_u8(60 + i, 4096, top=top, bottom=bottom)
+        raws.append(np.ascontiguousarray(img[::-1, :, ::-1]).reshape(-1))          # BMP order: bottom-up BGR
+    eng = engine.PredictEngine(calc.model, 'cuda:0', chunk=2)
+    dev_raws = [torch.from_numpy(r).to(cuda_device) for r in raws]
+    counts, masks, heights = eng.run_device(dev_raws, exclude_nodes=False)
+    counts, masks, heights = counts.cpu(), masks.cpu(), heights.cpu().tolist()
+    host_raws = [torch.from_numpy(r).pin_memory() for r in raws]
+    masks_host = [torch.empty(1024 * 1024, dtype=torch.uint8).pin_memory() for _ in raws]
+    rows, counts_h, _ = eng.run_host(host_raws, masks_host, exclude_nodes=False)
+    assert rows == heights
+    for i, r in enumerate(dev_raws):
+        out, fl = ops.preprocess_4x(r, 4096, 4096, bgr=True, bottom_up=True)
+        first, last = fl.tolist()
+        assert last - first == heights[i]
+        img = out[:(last - first) * 1024 * 3].view(last - first, 1024, 3)
+        mask, cnt = calc.predict_array(img, excludes_nodes=False)
+        assert torch.equal(masks[i, :heights[i]], mask.cpu())
+        assert torch.equal(counts[i], cnt.cpu())
+        assert torch.equal(masks_host[i][:heights[i] * 1024].view(heights[i], 1024), mask.cpu())
+        assert counts_h[i].tolist() == cnt.cpu().tolist()
+
+
 def test_predict_pipeline_matches_oracle(cuda_device, synthetic_sd, tmp_path):
     """predict.py end to end on a tiny synthetic folder: processed PNGs, dual PNGs and CSV against the CPU oracle."""
     import neuralbarkcalculator_b200 as nbc
