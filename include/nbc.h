@@ -11,7 +11,9 @@
  *  - every launch function takes the CUDA stream (a cudaStream_t passed as void*) and is asynchronous;
  *  - every function returns 0 on success or a negative nbc_status; nbc_last_error() gives the text
  *    (thread-local).  There is NO CPU fallback: a missing GPU or a non-sm_100 device is an error.
- *  - activations are NHWC bf16, masks are u8 [N,H,W], logits are f32 planar [N,3,h,w].
+ *  - activations are NHWC 16-bit floats, masks are u8 [N,H,W], logits are f32 planar [N,3,h,w].
+ *  - `f16` arguments select the 16-bit storage format of activations and packed weights: 0 = bf16 (default),
+ *    1 = IEEE fp16 (same tensor-core rate, 3 more mantissa bits; see DESIGN.md "Numerics").
  */
 #ifndef NBC_H_
 #define NBC_H_
@@ -60,7 +62,7 @@ int nbc_trim_u8(const uint8_t* img, int H, int W, uint8_t* out, int32_t* first_l
  * Output: bf16 [Cout][kh][kw][cin_pad] with w * gamma/sqrt(var+eps) folded in (channels >= Cin zero), and
  * f32 bias[Cout] = beta - mean*gamma/sqrt(var+eps) (+ conv_bias * scale). */
 int nbc_fold_bn_pack(const float* w, const float* gamma, const float* beta, const float* mean, const float* var,
-                     const float* conv_bias, float eps, int Cout, int Cin, int kh, int kw, int cin_pad,
+                     const float* conv_bias, float eps, int Cout, int Cin, int kh, int kw, int cin_pad, int f16,
                      void* w_packed_bf16, float* bias_out, void* stream);
 
 /* ---- K2: one convolution layer, implicit GEMM  (every nn.Conv2d+BN(+ReLU)(+residual) of models.py:127-139) --
@@ -71,6 +73,7 @@ typedef struct {
   int32_t kh, kw, stride, pad, dil;
   int32_t relu;
   int32_t impl;
+  int32_t f16;
 } nbc_conv_desc;
 int nbc_conv_bf16(const nbc_conv_desc* desc, const void* x, const void* w_packed, const float* bias,
                   const void* residual, void* y, void* stream);
@@ -87,15 +90,15 @@ int nbc_stem_f32(const float* x_nchw, int N, int H, int W, const float* w_stem, 
  * workspace and the 7x7/2 conv runs as an implicit GEMM (K = 7 rows x 8 px x 4 ch = 224) on tcgen05.
  * w224: bf16 [64][7][8][4] from nbc_stem_pack_weights(w_stem f32 [64][7][7][3] BN-folded). */
 size_t nbc_stem_tc_workspace_bytes(int N, int H, int W);
-int nbc_stem_pack_weights(const float* w_stem_f32, void* w224_bf16, void* stream);
+int nbc_stem_pack_weights(const float* w_stem_f32, int f16, void* w224_bf16, void* stream);
 int nbc_stem_tc(const void* input, int input_kind, int N, int H, int W, const float* mean3_host,
-                const float* std3_host, const void* w224_bf16, const float* bias, void* workspace,
+                const float* std3_host, const void* w224_bf16, const float* bias, int f16, void* workspace,
                 size_t workspace_bytes, void* out, void* stream);
-int nbc_maxpool3x3s2_bf16(const void* x, int N, int H, int W, int C, void* y, void* stream);
+int nbc_maxpool3x3s2_bf16(const void* x, int N, int H, int W, int C, int f16, void* y, void* stream);
 
 /* ---- head tail: Dropout(eval)=identity + Conv2d(512,3,1)+bias  (models.py:113-124) -> f32 planar logits ------ */
-int nbc_head_1x1(const void* x_bf16, int64_t pixels_per_image, int N, int Cin, const float* w3xC, const float* bias3,
-                 float* logits_planar, void* stream);
+int nbc_head_1x1(const void* x_bf16, int64_t pixels_per_image, int N, int Cin, int f16, const float* w3xC,
+                 const float* bias3, float* logits_planar, void* stream);
 
 /* ---- K3: bicubic upsample (A=-0.75, align_corners=False) + argmax  (models.py:38-41, 270) -----------------------
  * logits: f32 [N,3,h,w] -> mask u8 [N,H,W] (ties -> lowest class).  nbc_upsample_bicubic writes the f32
@@ -134,7 +137,7 @@ int nbc_wce_fwd_bwd(const float* logits, const void* target, int target_is_i64, 
  * (backbone.conv1.weight, backbone.bn1.{weight,bias,running_mean,running_var,num_batches_tracked}, ...).
  * The plan folds BN, packs bf16 weights (owned by the plan) and keeps nothing else. */
 nbc_plan* nbc_plan_create(const void* const* tensors_host, int n_tensors, const float* mean3_host,
-                          const float* std3_host);
+                          const float* std3_host, int f16);
 void nbc_plan_destroy(nbc_plan* plan);
 size_t nbc_plan_workspace_bytes(const nbc_plan* plan, int N, int H, int W);
 /* input_kind 0: images u8 NHWC [N,H,W,3] (normalised inside with the plan's mean/std);

@@ -10,7 +10,7 @@ c_void_p, c_int, c_i64, c_size_t, c_float = C.c_void_p, C.c_int, C.c_int64, C.c_
 
 
 class ConvDesc(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ('N', 'H', 'W', 'Cin', 'Cout', 'kh', 'kw', 'stride', 'pad', 'dil', 'relu', 'impl')]
+    _fields_ = [(n, C.c_int32) for n in ('N', 'H', 'W', 'Cin', 'Cout', 'kh', 'kw', 'stride', 'pad', 'dil', 'relu', 'impl', 'f16')]
 
 
 # name -> (restype, argtypes); kept in one table so tests can check it against include/nbc.h
@@ -22,16 +22,16 @@ SIGNATURES = {
     'nbc_preprocess_workspace_bytes': (c_size_t, [c_int, c_int]),
     'nbc_preprocess_4x_u8': (c_int, [c_void_p, c_int, c_int, c_i64, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'nbc_trim_u8': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    'nbc_fold_bn_pack': (c_int, [c_void_p] * 6 + [c_float, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'nbc_fold_bn_pack': (c_int, [c_void_p] * 6 + [c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'nbc_conv_bf16': (c_int, [C.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'nbc_stem_u8': (c_int, [c_void_p, c_int, c_int, c_int, C.POINTER(c_float), C.POINTER(c_float), c_void_p, c_void_p, c_void_p, c_void_p]),
     'nbc_stem_f32': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'nbc_stem_tc_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
-    'nbc_stem_pack_weights': (c_int, [c_void_p, c_void_p, c_void_p]),
+    'nbc_stem_pack_weights': (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     'nbc_stem_tc': (c_int, [c_void_p, c_int, c_int, c_int, c_int, C.POINTER(c_float), C.POINTER(c_float), c_void_p, c_void_p,
-                    c_void_p, c_size_t, c_void_p, c_void_p]),
-    'nbc_maxpool3x3s2_bf16': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    'nbc_head_1x1': (c_int, [c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+                    c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    'nbc_maxpool3x3s2_bf16': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'nbc_head_1x1': (c_int, [c_void_p, c_i64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'nbc_upsample_argmax': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'nbc_upsample_bicubic': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'nbc_upsample_argmax_ragged': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
@@ -42,7 +42,7 @@ SIGNATURES = {
                                       c_void_p]),
     'nbc_wce_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'nbc_wce_fwd_bwd': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    'nbc_plan_create': (c_void_p, [C.POINTER(c_void_p), c_int, C.POINTER(c_float), C.POINTER(c_float)]),
+    'nbc_plan_create': (c_void_p, [C.POINTER(c_void_p), c_int, C.POINTER(c_float), C.POINTER(c_float), c_int]),
     'nbc_plan_destroy': (None, [c_void_p]),
     'nbc_plan_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int]),
     'nbc_plan_forward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -47,8 +47,8 @@ __global__ void __launch_bounds__(256) fold_pack_kernel(const float* __restrict_
                                                         const float* __restrict__ beta, const float* __restrict__ mean,
                                                         const float* __restrict__ var, const float* __restrict__ cb,
                                                         float eps, int Cout, int Cin, int kh, int kw, int cin_pad,
-                                                        __nv_bfloat16* __restrict__ wp, float* __restrict__ bias,
-                                                        float* __restrict__ wp_f32) {
+                                                        unsigned short* __restrict__ wp, float* __restrict__ bias,
+                                                        float* __restrict__ wp_f32, int f16) {
   const int64_t total = (int64_t)Cout * kh * kw * cin_pad;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % cin_pad);
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) fold_pack_kernel(const float* __restrict_
     const float scale = gamma ? gamma[oc] / sqrtf(var[oc] + eps) : 1.f;
     float v = 0.f;
     if (c < Cin) v = w[(((int64_t)oc * Cin + c) * kh + ky) * kw + kx] * scale;
-    if (wp) wp[i] = __float2bfloat16_rn(v);
+    if (wp) wp[i] = cvt16(v, f16);
     if (wp_f32) wp_f32[i] = v;
     if (c == 0 && ky == 0 && kx == 0) {
       float b = gamma ? beta[oc] - mean[oc] * scale : 0.f;
@@ -72,11 +72,11 @@ __global__ void __launch_bounds__(256) fold_pack_kernel(const float* __restrict_
 
 int fold_pack(const float* w, const float* gamma, const float* beta, const float* mean, const float* var,
               const float* cb, float eps, int Cout, int Cin, int kh, int kw, int cin_pad, void* wp_bf16, float* wp_f32,
-              float* bias, cudaStream_t stream) {
+              float* bias, cudaStream_t stream, int f16) {
   const int64_t total = (int64_t)Cout * kh * kw * cin_pad;
   const int blocks = (int)(ceil_div64(total, 256) < 148 * 8 ? ceil_div64(total, 256) : 148 * 8);
   fold_pack_kernel<<<blocks, 256, 0, stream>>>(w, gamma, beta, mean, var, cb, eps, Cout, Cin, kh, kw, cin_pad,
-                                               reinterpret_cast<__nv_bfloat16*>(wp_bf16), bias, wp_f32);
+                                               reinterpret_cast<unsigned short*>(wp_bf16), bias, wp_f32, f16);
   NBC_CHECK_LAUNCH();
   return 0;
 }
@@ -112,21 +112,21 @@ extern "C" int nbc_device_check(int device) {
 
 extern "C" int nbc_fold_bn_pack(const float* w, const float* gamma, const float* beta, const float* mean,
                                 const float* var, const float* conv_bias, float eps, int Cout, int Cin, int kh, int kw,
-                                int cin_pad, void* w_packed_bf16, float* bias_out, void* stream) {
+                                int cin_pad, int f16, void* w_packed_bf16, float* bias_out, void* stream) {
   NBC_REQUIRE(w && w_packed_bf16 && bias_out, "nbc_fold_bn_pack: null pointer");
   NBC_REQUIRE((gamma != nullptr) == (beta != nullptr) && (gamma != nullptr) == (mean != nullptr) &&
                   (gamma != nullptr) == (var != nullptr),
               "nbc_fold_bn_pack: gamma/beta/mean/var must be all given or all NULL");
   NBC_REQUIRE(Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && cin_pad >= Cin, "nbc_fold_bn_pack: bad shape");
   return fold_pack(w, gamma, beta, mean, var, conv_bias, eps, Cout, Cin, kh, kw, cin_pad, w_packed_bf16, nullptr,
-                   bias_out, reinterpret_cast<cudaStream_t>(stream));
+                   bias_out, reinterpret_cast<cudaStream_t>(stream), f16 ? 1 : 0);
 }
 
 extern "C" int nbc_conv_bf16(const nbc_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                              const void* residual, void* y, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   NBC_REQUIRE(d && x && w_packed && bias && y, "nbc_conv_bf16: null pointer");
-  ConvGeom g{d->N, d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, d->stride, d->pad, d->dil, d->relu};
+  ConvGeom g{d->N, d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, d->stride, d->pad, d->dil, d->relu, d->f16 ? 1 : 0};
   NBC_REQUIRE(g.N > 0 && g.H > 0 && g.W > 0 && g.Ho() > 0 && g.Wo() > 0, "nbc_conv_bf16: bad shape");
   const bool tc_ok = conv_tc_supported(g);
   if (d->impl == 1 || (d->impl == 0 && tc_ok)) return conv_tc(g, x, w_packed, bias, residual, y, stream);

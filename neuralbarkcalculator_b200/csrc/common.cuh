@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -205,6 +206,10 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with A = B = fp16 (format code 0)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -212,6 +217,25 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+// 16-bit storage format of activations and weights: f16 == 0 -> bf16 (default), f16 == 1 -> IEEE fp16.  Both feed
+// tcgen05 kind::f16 at the same rate; fp16 keeps 3 more mantissa bits (see DESIGN.md "Numerics").
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi, int f16) {
+  if (f16) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float lo16(uint32_t v, int f16) {
+  return f16 ? __half2float(__ushort_as_half((unsigned short)(v & 0xFFFFu))) : bf16lo(v);
+}
+__device__ __forceinline__ float hi16(uint32_t v, int f16) {
+  return f16 ? __half2float(__ushort_as_half((unsigned short)(v >> 16))) : bf16hi(v);
+}
+__device__ __forceinline__ unsigned short cvt16(float x, int f16) {
+  return f16 ? __half_as_ushort(__float2half_rn(x)) : __bfloat16_as_ushort(__float2bfloat16_rn(x));
+}
 
 #endif  // __CUDACC__
 }  // namespace nbc

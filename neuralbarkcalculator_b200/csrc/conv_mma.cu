@@ -16,7 +16,7 @@ struct ConvMmaParams {
   const __nv_bfloat16* residual;
   __nv_bfloat16* y;
   int N, H, W, Cin, Cout, Ho, Wo;
-  int kh, kw, stride, pad, dil, relu;
+  int kh, kw, stride, pad, dil, relu, f16;
   int64_t M;  // N*Ho*Wo
 };
 
@@ -38,6 +38,12 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -126,7 +132,12 @@ __global__ void __launch_bounds__(256) conv_mma_kernel(const ConvMmaParams p) {
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) mma_bf16(acc[i][j], a[i], b[j][0], b[j][1]);
+        for (int j = 0; j < 4; ++j) {
+          if (p.f16)
+            mma_f16(acc[i][j], a[i], b[j][0], b[j][1]);
+          else
+            mma_bf16(acc[i][j], a[i], b[j][0], b[j][1]);
+        }
     }
     __syncthreads();
   }
@@ -147,14 +158,14 @@ __global__ void __launch_bounds__(256) conv_mma_kernel(const ConvMmaParams p) {
         const int64_t off = m * p.Cout + col;
         if (p.residual) {
           const uint32_t rv = __ldg(reinterpret_cast<const uint32_t*>(p.residual + off));
-          v0 += bf16lo(rv);
-          v1 += bf16hi(rv);
+          v0 += lo16(rv, p.f16);
+          v1 += hi16(rv, p.f16);
         }
         if (p.relu) {
           v0 = fmaxf(v0, 0.f);
           v1 = fmaxf(v1, 0.f);
         }
-        *reinterpret_cast<uint32_t*>(p.y + off) = pack_bf16x2(v0, v1);
+        *reinterpret_cast<uint32_t*>(p.y + off) = pack16x2(v0, v1, p.f16);
       }
     }
 }
@@ -174,7 +185,7 @@ int conv_mma(const ConvGeom& g, const void* x, const void* w, const float* bias,
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
   p.N = g.N, p.H = g.H, p.W = g.W, p.Cin = g.Cin, p.Cout = g.Cout, p.Ho = g.Ho(), p.Wo = g.Wo();
-  p.kh = g.kh, p.kw = g.kw, p.stride = g.stride, p.pad = g.pad, p.dil = g.dil, p.relu = g.relu;
+  p.kh = g.kh, p.kw = g.kw, p.stride = g.stride, p.pad = g.pad, p.dil = g.dil, p.relu = g.relu, p.f16 = g.f16;
   p.M = (int64_t)g.N * p.Ho * p.Wo;
   dim3 grid((unsigned)ceil_div64(p.M, MM_BM), (unsigned)(g.Cout / MM_BN));
   conv_mma_kernel<<<grid, 256, 0, stream>>>(p);

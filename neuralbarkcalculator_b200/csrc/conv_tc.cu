@@ -32,6 +32,7 @@ struct ConvTcParams {
   int num_m_tiles, num_n_tiles;
   int n_taps, cblocks;
   int relu;
+  int f16;  // operand / output format: 0 bf16, 1 fp16
   // ragged batches: valid_h[img] = number of valid OUTPUT rows of image img (nullptr: all rows valid).  Rows at or
   // beyond it are written as zeros for kRaggedHalo rows (the zero padding the next layer reads) and skipped after.
   const int* valid_h;
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      const uint32_t idesc = p.f16 ? umma_idesc_f16(128, BN) : umma_idesc_bf16(128, BN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         if (p.valid_h != nullptr) {
@@ -250,15 +251,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             if (has_res && live[j]) {
               const uint32_t rv[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
 #pragma unroll
-              for (int k = 0; k < 4; ++k) v[2 * k] += bf16lo(rv[k]), v[2 * k + 1] += bf16hi(rv[k]);
+              for (int k = 0; k < 4; ++k) v[2 * k] += lo16(rv[k], p.f16), v[2 * k + 1] += hi16(rv[k], p.f16);
             }
             if (p.relu) {
 #pragma unroll
               for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
             }
             *reinterpret_cast<uint4*>(p.out + offs[j] + c) =
-                live[j] ? make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                     pack_bf16x2(v[6], v[7]))
+                live[j] ? make_uint4(pack16x2(v[0], v[1], p.f16), pack16x2(v[2], v[3], p.f16), pack16x2(v[4], v[5], p.f16),
+                                     pack16x2(v[6], v[7], p.f16))
                         : make_uint4(0u, 0u, 0u, 0u);
           }
         }
@@ -374,6 +375,7 @@ static int build_launch(const ConvGeom& g, const void* x, const void* w, const f
   p.n_taps = g.kh * g.kw;
   p.cblocks = g.Cin / 64;
   p.relu = g.relu;
+  p.f16 = g.f16;
   p.bias = bias;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.out = reinterpret_cast<__nv_bfloat16*>(y);
@@ -441,10 +443,11 @@ static int launch_bn(const ConvTcLaunch& L, cudaStream_t stream) {
 // The windows of neighbouring outputs overlap (stride 16 B, extent 64 B): the tensor map simply describes that
 // address function.  Even / odd padded rows are two lattices, exactly like the stride-2 convolutions.
 int conv_tc_prepare_stem(int N, int Ho, int Wo, int Hp, int Wp, const void* padded, const void* w224, const float* bias,
-                         void* y, ConvTcPrepared* out, const int* valid_h) {
+                         void* y, ConvTcPrepared* out, const int* valid_h, int f16) {
   ConvTcLaunch* L = reinterpret_cast<ConvTcLaunch*>(out->storage);
   ConvTcParams& p = L->p;
   memset(&p, 0, sizeof(p));
+  p.f16 = f16;
   choose_tile(Ho, Wo, &p);
   p.N = N, p.Ho = Ho, p.Wo = Wo, p.Cout = 64;
   p.num_m_tiles = N * p.tiles_w * p.tiles_h;

@@ -15,7 +15,7 @@ namespace nbc {
 template <int kIters>
 __global__ void __launch_bounds__(256) head1x1_kernel(const __nv_bfloat16* __restrict__ x, int64_t P, int N, int Cin,
                                                       const float* __restrict__ w, const float* __restrict__ bias,
-                                                      float* __restrict__ logits) {
+                                                      float* __restrict__ logits, int f16) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) head1x1_kernel(const __nv_bfloat16* __res
       const uint32_t u[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float f0 = bf16lo(u[k]), f1 = bf16hi(u[k]);
+        const float f0 = lo16(u[k], f16), f1 = hi16(u[k], f16);
         a0 = fmaf(f0, wr[it][0][2 * k], a0), a0 = fmaf(f1, wr[it][0][2 * k + 1], a0);
         a1 = fmaf(f0, wr[it][1][2 * k], a1), a1 = fmaf(f1, wr[it][1][2 * k + 1], a1);
         a2 = fmaf(f0, wr[it][2][2 * k], a2), a2 = fmaf(f1, wr[it][2][2 * k + 1], a2);
@@ -182,9 +182,9 @@ extern "C" int nbc_upsample_argmax_ragged(const float* logits, int N, int hc, in
   return 0;
 }
 
-extern "C" int nbc_head_1x1(const void* x_bf16, int64_t pixels_per_image, int N, int Cin, const float* w3xC,
-                            const float* bias3, float* logits_planar, void* stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+namespace nbc {
+int head_1x1(const void* x_bf16, int64_t pixels_per_image, int N, int Cin, const float* w3xC, const float* bias3,
+             float* logits_planar, int f16, cudaStream_t stream) {
   NBC_REQUIRE(x_bf16 && w3xC && bias3 && logits_planar, "nbc_head_1x1: null pointer");
   NBC_REQUIRE((Cin == 256 || Cin == 512 || Cin == 1024) && N > 0 && pixels_per_image > 0,
               "nbc_head_1x1: Cin must be 256, 512 or 1024 (got %d)", Cin);
@@ -193,13 +193,20 @@ extern "C" int nbc_head_1x1(const void* x_bf16, int64_t pixels_per_image, int N,
   const int blocks = (int)(want < 148 * 8 ? (want < 1 ? 1 : want) : 148 * 8);
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x_bf16);
   if (Cin == 256)
-    head1x1_kernel<1><<<blocks, 256, 0, stream>>>(xb, pixels_per_image, N, Cin, w3xC, bias3, logits_planar);
+    head1x1_kernel<1><<<blocks, 256, 0, stream>>>(xb, pixels_per_image, N, Cin, w3xC, bias3, logits_planar, f16);
   else if (Cin == 512)
-    head1x1_kernel<2><<<blocks, 256, 0, stream>>>(xb, pixels_per_image, N, Cin, w3xC, bias3, logits_planar);
+    head1x1_kernel<2><<<blocks, 256, 0, stream>>>(xb, pixels_per_image, N, Cin, w3xC, bias3, logits_planar, f16);
   else
-    head1x1_kernel<4><<<blocks, 256, 0, stream>>>(xb, pixels_per_image, N, Cin, w3xC, bias3, logits_planar);
+    head1x1_kernel<4><<<blocks, 256, 0, stream>>>(xb, pixels_per_image, N, Cin, w3xC, bias3, logits_planar, f16);
   NBC_CHECK_LAUNCH();
   return 0;
+}
+}  // namespace nbc
+
+extern "C" int nbc_head_1x1(const void* x_bf16, int64_t pixels_per_image, int N, int Cin, int f16, const float* w3xC,
+                            const float* bias3, float* logits_planar, void* stream) {
+  return head_1x1(x_bf16, pixels_per_image, N, Cin, w3xC, bias3, logits_planar, f16 ? 1 : 0,
+                  reinterpret_cast<cudaStream_t>(stream));
 }
 
 static int upsample_common(const float* logits, int N, int C, int h, int w, int H, int W, uint8_t* mask, float* out,

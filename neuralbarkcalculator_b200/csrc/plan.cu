@@ -51,6 +51,7 @@ struct nbc_plan {
   float* cls_b = nullptr;
   std::vector<void*> allocs;
   int impl = 0;
+  int f16 = 0;   // 16-bit storage format: 0 bf16 (default), 1 fp16
   // cached launch lists (tensor maps are encoded once per shape / workspace): key = (N, H, W, workspace, impl)
   typedef std::tuple<int, int, int, void*, int, int> Key;   // N, H, W, workspace, impl, ragged
   std::map<Key, std::vector<nbc::Step>> cache;
@@ -75,7 +76,8 @@ static int make_conv(nbc_plan* p, const void* const* t, int Cin, int Cout, int k
   if (rc) return rc;
   return fold_pack(reinterpret_cast<const float*>(t[0]), reinterpret_cast<const float*>(t[1]),
                    reinterpret_cast<const float*>(t[2]), reinterpret_cast<const float*>(t[3]),
-                   reinterpret_cast<const float*>(t[4]), nullptr, 1e-5f, Cout, Cin, k, k, Cin, L->w, nullptr, L->bias, 0);
+                   reinterpret_cast<const float*>(t[4]), nullptr, 1e-5f, Cout, Cin, k, k, Cin, L->w, nullptr, L->bias, 0,
+                   p->f16);
 }
 
 struct Dims {
@@ -108,7 +110,7 @@ static int add_conv(nbc_plan* p, const ConvLayer& L, int N, int H, int W, const 
                     const char* name, int* Ho, int* Wo, const int* levels = nullptr, int* level = nullptr) {
   Step s;
   memset(&s.prep, 0, sizeof(s.prep));
-  s.g = ConvGeom{N, H, W, L.Cin, L.Cout, L.k, L.k, L.stride, L.pad, L.dil, L.relu};
+  s.g = ConvGeom{N, H, W, L.Cin, L.Cout, L.k, L.k, L.stride, L.pad, L.dil, L.relu, p->f16};
   s.x = x, s.w = L.w, s.bias = L.bias, s.residual = residual, s.y = y, s.name = name;
   const bool tc = (p->impl != 2) && conv_tc_supported(s.g);
   s.kind = tc ? 2 : 3;
@@ -160,7 +162,7 @@ static int build_steps(nbc_plan* p, int N, int H, int W, void* workspace, bool r
     if (p->impl != 2) {
       s.kind = 5;  // tensor-core stem
       int rc = conv_tc_prepare_stem(N, d.H2, d.W2, 2 * d.H2 + 5, 2 * d.W2 + 6, t2, p->stem_w224, p->stem_b, bufB, &s.prep,
-                                    ragged ? levels + N : nullptr);
+                                    ragged ? levels + N : nullptr, p->f16);
       if (rc) return rc;
     }
     s.w = levels;   // w slot of the stem / maxpool steps = ragged level table (or nullptr)
@@ -222,18 +224,19 @@ static int run_step(nbc_plan* p, const Step& s, const void* input, int input_kin
                          p->stem_b, s.y, stream);
     case 5: {
       int rc = stem_tc_pad(input, input_kind, s.g.N, s.g.H, s.g.W, p->mean, p->std, const_cast<void*>(s.residual), stream,
-                           reinterpret_cast<const int*>(s.w));
+                           reinterpret_cast<const int*>(s.w), p->f16);
       if (rc) return rc;
       return conv_tc_run(&s.prep, stream);
     }
     case 1:
       if (s.w != nullptr)
-        return maxpool_ragged(s.x, s.g.N, s.g.H, s.g.W, 64, s.y, reinterpret_cast<const int*>(s.w) + 2 * (size_t)s.g.N, stream);
-      return nbc_maxpool3x3s2_bf16(s.x, s.g.N, s.g.H, s.g.W, 64, s.y, stream);
+        return maxpool_ragged(s.x, s.g.N, s.g.H, s.g.W, 64, s.y, reinterpret_cast<const int*>(s.w) + 2 * (size_t)s.g.N, stream,
+                              p->f16);
+      return nbc_maxpool3x3s2_bf16(s.x, s.g.N, s.g.H, s.g.W, 64, p->f16, s.y, stream);
     case 2: return conv_tc_run(&s.prep, stream);
     case 3: return conv_mma(s.g, s.x, s.w, s.bias, s.residual, s.y, stream);
     case 4:
-      return nbc_head_1x1(s.x, (int64_t)s.g.H * s.g.W, s.g.N, 512, p->cls_w, p->cls_b, logits, stream);
+      return head_1x1(s.x, (int64_t)s.g.H * s.g.W, s.g.N, 512, p->cls_w, p->cls_b, logits, p->f16, stream);
   }
   return NBC_ERR_INVALID;
 }
@@ -271,7 +274,7 @@ static int ensure_steps(nbc_plan* p, const void* images, int input_kind, int N, 
 using namespace nbc;
 
 extern "C" nbc_plan* nbc_plan_create(const void* const* t, int n_tensors, const float* mean3_host,
-                                     const float* std3_host) {
+                                     const float* std3_host, int f16) {
   if (!t || n_tensors != 326 || !mean3_host || !std3_host) {
     set_error("nbc_plan_create: expected the 326 state_dict tensors of fcn_resnet50 (got %d)", n_tensors);
     return nullptr;
@@ -282,6 +285,7 @@ extern "C" nbc_plan* nbc_plan_create(const void* const* t, int n_tensors, const 
       return nullptr;
     }
   nbc_plan* p = new nbc_plan();
+  p->f16 = f16 ? 1 : 0;
   for (int i = 0; i < 3; ++i) p->mean[i] = mean3_host[i], p->std[i] = std3_host[i];
   int rc = 0;
   int idx = 0;
@@ -293,7 +297,7 @@ extern "C" nbc_plan* nbc_plan_create(const void* const* t, int n_tensors, const 
                    reinterpret_cast<const float*>(t[2]), reinterpret_cast<const float*>(t[3]),
                    reinterpret_cast<const float*>(t[4]), nullptr, 1e-5f, 64, 3, 7, 7, 3, nullptr, p->stem_w, p->stem_b, 0);
   if (!rc) rc = dev_alloc(p, reinterpret_cast<void**>(&p->stem_w224), 64 * 224 * 2);
-  if (!rc) rc = nbc_stem_pack_weights(p->stem_w, p->stem_w224, 0);
+  if (!rc) rc = nbc_stem_pack_weights(p->stem_w, p->f16, p->stem_w224, 0);
   idx = 6;
   const int nblocks[4] = {3, 4, 6, 3};
   const int planes[4] = {64, 128, 256, 512};

@@ -24,6 +24,7 @@ struct StemParams {
   __nv_bfloat16* out; // [N][Ho][Wo][64]
   int N, H, W, Ho, Wo;
   float mean[3], std[3];
+  int f16;  // 16-bit output format: 0 bf16, 1 fp16
 };
 
 template <bool kF32>
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const StemParams p) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int c = q * 8 + 2 * k;
-        r[k] = pack_bf16x2(fmaxf(acc[c] + __ldg(p.bias + c), 0.f), fmaxf(acc[c + 1] + __ldg(p.bias + c + 1), 0.f));
+        r[k] = pack16x2(fmaxf(acc[c] + __ldg(p.bias + c), 0.f), fmaxf(acc[c + 1] + __ldg(p.bias + c + 1), 0.f), p.f16);
       }
       o[q] = make_uint4(r[0], r[1], r[2], r[3]);
     }
@@ -121,24 +122,24 @@ __global__ void __launch_bounds__(256) stem_pad_kernel(const StemParams p, int H
           v[ch] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)s[ch], 255.f), p.mean[ch]), p.std[ch]);
       }
     }
-    padded[i] = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], 0.f));
+    padded[i] = make_uint2(pack16x2(v[0], v[1], p.f16), pack16x2(v[2], 0.f, p.f16));
   }
 }
 
 // stem weights f32 [64][7][7][3] (BN folded) -> bf16 [64][7][8][4], zero for kx == 7 or c == 3  (K = 224)
-__global__ void stem_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+__global__ void stem_pack_kernel(const float* __restrict__ w, unsigned short* __restrict__ out, int f16) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 64 * 224) return;
   const int c = i & 3, kx = (i >> 2) & 7, ky = (i >> 5) % 7, oc = i / 224;
   float v = 0.f;
   if (c < 3 && kx < 7) v = w[((oc * 7 + ky) * 7 + kx) * 3 + c];
-  out[i] = __float2bfloat16_rn(v);
+  out[i] = cvt16(v, f16);
 }
 
 // maxpool 3x3 stride 2 pad 1 (padding = -inf), bf16 NHWC, 8 channels per thread
 __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C,
                                                       int Ho, int Wo, __nv_bfloat16* __restrict__ y,
-                                                      const int* __restrict__ valid_h) {
+                                                      const int* __restrict__ valid_h, int f16) {
   const int cg = C >> 3;
   const int64_t total = (int64_t)N * Ho * Wo * cg;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -155,10 +156,9 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __res
         continue;
       }
     }
-    __nv_bfloat162 m[4];
-    const __nv_bfloat162 ninf = __floats2bfloat162_rn(-INFINITY, -INFINITY);
+    float m[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) m[k] = ninf;
+    for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
 #pragma unroll
     for (int dy = -1; dy <= 1; ++dy) {
       const int h = 2 * ho + dy;
@@ -168,12 +168,14 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __res
         const int w = 2 * wo + dx;
         if (w < 0 || w >= W) continue;
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)n * H + h) * W + w) * C + c8 * 8));
-        const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) m[k] = __hmax2(m[k], v2[k]);
+        for (int k = 0; k < 4; ++k) m[2 * k] = fmaxf(m[2 * k], lo16(u[k], f16)), m[2 * k + 1] = fmaxf(m[2 * k + 1], hi16(u[k], f16));
       }
     }
-    *reinterpret_cast<uint4*>(y + (((int64_t)n * Ho + ho) * Wo + wo) * C + c8 * 8) = *reinterpret_cast<uint4*>(m);
+    // the maxima are values that were stored in this format: converting back is exact
+    *reinterpret_cast<uint4*>(y + (((int64_t)n * Ho + ho) * Wo + wo) * C + c8 * 8) =
+        make_uint4(pack16x2(m[0], m[1], f16), pack16x2(m[2], m[3], f16), pack16x2(m[4], m[5], f16), pack16x2(m[6], m[7], f16));
   }
 }
 
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __res
 using namespace nbc;
 
 static int stem_launch(const uint8_t* img, const float* xf, int N, int H, int W, const float* mean3, const float* std3,
-                       const float* w_stem, const float* bias, void* out, cudaStream_t stream) {
+                       const float* w_stem, const float* bias, void* out, cudaStream_t stream, int f16 = 0) {
   NBC_REQUIRE((img || xf) && w_stem && bias && out, "nbc_stem: null pointer");
   NBC_REQUIRE(N > 0 && H > 0 && W > 0 && N <= 65535, "nbc_stem: bad shape");
   static bool attr_set = false;
@@ -194,6 +196,7 @@ static int stem_launch(const uint8_t* img, const float* xf, int N, int H, int W,
   StemParams p;
   p.img = img, p.xf = xf, p.w = w_stem, p.bias = bias, p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.N = N, p.H = H, p.W = W, p.Ho = (H + 6 - 7) / 2 + 1, p.Wo = (W + 6 - 7) / 2 + 1;
+  p.f16 = f16;
   for (int i = 0; i < 3; ++i) p.mean[i] = mean3 ? mean3[i] : 0.f, p.std[i] = std3 ? std3[i] : 1.f;
   dim3 grid(ceil_div(p.Wo, ST_T), ceil_div(p.Ho, ST_T), N);
   if (xf)
@@ -223,19 +226,20 @@ extern "C" size_t nbc_stem_tc_workspace_bytes(int N, int H, int W) {
   return align_up((size_t)N * (2 * Ho + 5) * (2 * Wo + 6) * 8, 1024);
 }
 
-extern "C" int nbc_stem_pack_weights(const float* w_stem_f32, void* w224_bf16, void* stream) {
+extern "C" int nbc_stem_pack_weights(const float* w_stem_f32, int f16, void* w224_bf16, void* stream) {
   NBC_REQUIRE(w_stem_f32 && w224_bf16, "nbc_stem_pack_weights: null pointer");
   stem_pack_kernel<<<ceil_div(64 * 224, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      w_stem_f32, reinterpret_cast<__nv_bfloat16*>(w224_bf16));
+      w_stem_f32, reinterpret_cast<unsigned short*>(w224_bf16), f16 ? 1 : 0);
   NBC_CHECK_LAUNCH();
   return 0;
 }
 
 namespace nbc {
 int stem_tc_pad(const void* input, int input_kind, int N, int H, int W, const float* mean3, const float* std3, void* padded,
-                cudaStream_t stream, const int* valid_h) {
+                cudaStream_t stream, const int* valid_h, int f16) {
   StemParams p;
   memset(&p, 0, sizeof(p));
+  p.f16 = f16;
   p.img = input_kind == 0 ? reinterpret_cast<const uint8_t*>(input) : nullptr;
   p.xf = input_kind == 1 ? reinterpret_cast<const float*>(input) : nullptr;
   p.N = N, p.H = H, p.W = W, p.Ho = (H - 1) / 2 + 1, p.Wo = (W - 1) / 2 + 1;
@@ -253,7 +257,7 @@ int stem_tc_pad(const void* input, int input_kind, int N, int H, int W, const fl
 }  // namespace nbc
 
 extern "C" int nbc_stem_tc(const void* input, int input_kind, int N, int H, int W, const float* mean3_host,
-                           const float* std3_host, const void* w224_bf16, const float* bias, void* workspace,
+                           const float* std3_host, const void* w224_bf16, const float* bias, int f16, void* workspace,
                            size_t workspace_bytes, void* out, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   NBC_REQUIRE(input && w224_bf16 && bias && workspace && out, "nbc_stem_tc: null pointer");
@@ -266,15 +270,15 @@ extern "C" int nbc_stem_tc(const void* input, int input_kind, int N, int H, int 
     return NBC_ERR_WORKSPACE;
   }
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  int rc = stem_tc_pad(input, input_kind, N, H, W, mean3_host, std3_host, workspace, stream, nullptr);
+  int rc = stem_tc_pad(input, input_kind, N, H, W, mean3_host, std3_host, workspace, stream, nullptr, f16 ? 1 : 0);
   if (rc) return rc;
   ConvTcPrepared prep;
-  rc = conv_tc_prepare_stem(N, Ho, Wo, 2 * Ho + 5, 2 * Wo + 6, workspace, w224_bf16, bias, out, &prep);
+  rc = conv_tc_prepare_stem(N, Ho, Wo, 2 * Ho + 5, 2 * Wo + 6, workspace, w224_bf16, bias, out, &prep, nullptr, f16 ? 1 : 0);
   if (rc) return rc;
   return conv_tc_run(&prep, stream);
 }
 
-extern "C" int nbc_maxpool3x3s2_bf16(const void* x, int N, int H, int W, int C, void* y, void* stream_) {
+extern "C" int nbc_maxpool3x3s2_bf16(const void* x, int N, int H, int W, int C, int f16, void* y, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   NBC_REQUIRE(x && y, "nbc_maxpool3x3s2_bf16: null pointer");
   NBC_REQUIRE(C % 8 == 0 && N > 0 && H > 0 && W > 0, "nbc_maxpool3x3s2_bf16: bad shape");
@@ -282,18 +286,18 @@ extern "C" int nbc_maxpool3x3s2_bf16(const void* x, int N, int H, int W, int C, 
   const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
   const int blocks = (int)(ceil_div64(total, 256) < 148 * 16 ? ceil_div64(total, 256) : 148 * 16);
   maxpool_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, Ho, Wo,
-                                             reinterpret_cast<__nv_bfloat16*>(y), nullptr);
+                                             reinterpret_cast<__nv_bfloat16*>(y), nullptr, f16 ? 1 : 0);
   NBC_CHECK_LAUNCH();
   return 0;
 }
 
 namespace nbc {
-int maxpool_ragged(const void* x, int N, int H, int W, int C, void* y, const int* valid_h, cudaStream_t stream) {
+int maxpool_ragged(const void* x, int N, int H, int W, int C, void* y, const int* valid_h, cudaStream_t stream, int f16) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
   const int blocks = (int)(ceil_div64(total, 256) < 148 * 16 ? ceil_div64(total, 256) : 148 * 16);
   maxpool_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, Ho, Wo,
-                                             reinterpret_cast<__nv_bfloat16*>(y), valid_h);
+                                             reinterpret_cast<__nv_bfloat16*>(y), valid_h, f16);
   NBC_CHECK_LAUNCH();
   return 0;
 }

@@ -29,6 +29,17 @@ def _contig(t, dtype, name):
     return t if t.is_contiguous() else t.contiguous()
 
 
+HALF_DTYPES = {'bf16': torch.bfloat16, 'fp16': torch.float16}
+
+
+def _half(t, name):
+    """16-bit activation tensor: bf16 or fp16.  Returns (contiguous tensor, f16 flag)."""
+    _dev(t, name)
+    if t.dtype not in (torch.bfloat16, torch.float16):
+        raise RuntimeError('%s must be bfloat16 or float16 (got %s)' % (name, t.dtype))
+    return (t if t.is_contiguous() else t.contiguous()), (1 if t.dtype == torch.float16 else 0)
+
+
 # ---- K1 -------------------------------------------------------------------------------------------------------
 def preprocess_4x(raw, H, W, pitch=None, bgr=False, bottom_up=False, workspace=None):
     """raw: u8 CUDA tensor holding an H x W x 3 pixel array (row pitch ``pitch`` bytes).
@@ -64,8 +75,8 @@ def trim_u8(img):
 
 
 # ---- weights / single layers (unit-test surface) --------------------------------------------------------------------
-def fold_bn_pack(weight, bn=None, conv_bias=None, eps=1e-5, cin_pad=None):
-    """weight f32 OIHW (+ optional (gamma, beta, mean, var)) -> (bf16 [Cout,kh,kw,cin_pad], f32 bias[Cout])."""
+def fold_bn_pack(weight, bn=None, conv_bias=None, eps=1e-5, cin_pad=None, dtype=torch.bfloat16):
+    """weight f32 OIHW (+ optional (gamma, beta, mean, var)) -> (bf16|fp16 [Cout,kh,kw,cin_pad], f32 bias[Cout])."""
     lib = _lib.load()
     weight = _contig(weight, torch.float32, 'weight')
     Cout, Cin, kh, kw = weight.shape
@@ -75,18 +86,19 @@ def fold_bn_pack(weight, bn=None, conv_bias=None, eps=1e-5, cin_pad=None):
         g, b, m, v = [_contig(t, torch.float32, 'bn') for t in bn]
     cb = _contig(conv_bias, torch.float32, 'conv_bias') if conv_bias is not None else None
     with torch.cuda.device(weight.device):
-        wp = torch.empty((Cout, kh, kw, cin_pad), dtype=torch.bfloat16, device=weight.device)
+        wp = torch.empty((Cout, kh, kw, cin_pad), dtype=dtype, device=weight.device)
         bias = torch.empty(Cout, dtype=torch.float32, device=weight.device)
         _lib.check(lib.nbc_fold_bn_pack(_ptr(weight), _ptr(g), _ptr(b), _ptr(m), _ptr(v), _ptr(cb), eps, Cout, Cin, kh, kw,
-                                        cin_pad, _ptr(wp), _ptr(bias), _stream(weight.device)), 'nbc_fold_bn_pack')
+                                        cin_pad, 1 if dtype == torch.float16 else 0, _ptr(wp), _ptr(bias),
+                                        _stream(weight.device)), 'nbc_fold_bn_pack')
     return wp, bias
 
 
 def conv_bf16(x, w_packed, bias, stride=1, pad=0, dil=1, relu=False, residual=None, impl=0):
-    """x bf16 NHWC [N,H,W,Cin]; w_packed bf16 [Cout,kh,kw,Cin]; -> bf16 NHWC [N,Ho,Wo,Cout]."""
+    """x bf16|fp16 NHWC [N,H,W,Cin]; w_packed same dtype [Cout,kh,kw,Cin]; -> NHWC [N,Ho,Wo,Cout] of that dtype."""
     lib = _lib.load()
-    x = _contig(x, torch.bfloat16, 'x')
-    w_packed = _contig(w_packed, torch.bfloat16, 'w_packed')
+    x, f16 = _half(x, 'x')
+    w_packed = _contig(w_packed, x.dtype, 'w_packed')
     bias = _contig(bias, torch.float32, 'bias')
     N, H, W, Cin = x.shape
     Cout, kh, kw, cin2 = w_packed.shape
@@ -95,12 +107,12 @@ def conv_bf16(x, w_packed, bias, stride=1, pad=0, dil=1, relu=False, residual=No
     Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
     Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
     if residual is not None:
-        residual = _contig(residual, torch.bfloat16, 'residual')
+        residual = _contig(residual, x.dtype, 'residual')
         if tuple(residual.shape) != (N, Ho, Wo, Cout):
             raise RuntimeError('conv_bf16: residual shape mismatch')
     with torch.cuda.device(x.device):
-        y = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
-        d = _lib.ConvDesc(N, H, W, Cin, Cout, kh, kw, stride, pad, dil, 1 if relu else 0, impl)
+        y = torch.empty((N, Ho, Wo, Cout), dtype=x.dtype, device=x.device)
+        d = _lib.ConvDesc(N, H, W, Cin, Cout, kh, kw, stride, pad, dil, 1 if relu else 0, impl, f16)
         _lib.check(lib.nbc_conv_bf16(C.byref(d), _ptr(x), _ptr(w_packed), _ptr(bias), _ptr(residual), _ptr(y),
                                      _stream(x.device)), 'nbc_conv_bf16')
     return y
@@ -130,7 +142,7 @@ def stem_f32(x, w_stem, bias):
     return out
 
 
-def stem_tc(inp, mean, std, w_stem, bias):
+def stem_tc(inp, mean, std, w_stem, bias, dtype=torch.bfloat16):
     """Tensor-core stem: inp u8 NHWC or f32 NCHW; w_stem f32 [64,7,7,3] (BN folded) -> bf16 NHWC [N,H/2,W/2,64]."""
     lib = _lib.load()
     _dev(inp, 'input')
@@ -144,34 +156,35 @@ def stem_tc(inp, mean, std, w_stem, bias):
     m3 = (C.c_float * 3)(*mean)
     s3 = (C.c_float * 3)(*std)
     with torch.cuda.device(inp.device):
-        w224 = torch.empty(64 * 224, dtype=torch.bfloat16, device=inp.device)
-        _lib.check(lib.nbc_stem_pack_weights(_ptr(_contig(w_stem, torch.float32, 'w_stem')), _ptr(w224), _stream(inp.device)),
+        f16 = 1 if dtype == torch.float16 else 0
+        w224 = torch.empty(64 * 224, dtype=dtype, device=inp.device)
+        _lib.check(lib.nbc_stem_pack_weights(_ptr(_contig(w_stem, torch.float32, 'w_stem')), f16, _ptr(w224), _stream(inp.device)),
                    'nbc_stem_pack_weights')
         ws = torch.empty(lib.nbc_stem_tc_workspace_bytes(N, H, W), dtype=torch.uint8, device=inp.device)
-        out = torch.empty((N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64), dtype=torch.bfloat16, device=inp.device)
+        out = torch.empty((N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64), dtype=dtype, device=inp.device)
         _lib.check(lib.nbc_stem_tc(_ptr(inp), kind, N, H, W, m3, s3, _ptr(w224), _ptr(_contig(bias, torch.float32, 'bias')),
-                                   _ptr(ws), ws.numel(), _ptr(out), _stream(inp.device)), 'nbc_stem_tc')
+                                   f16, _ptr(ws), ws.numel(), _ptr(out), _stream(inp.device)), 'nbc_stem_tc')
     return out
 
 
 def maxpool3x3s2(x):
     lib = _lib.load()
-    x = _contig(x, torch.bfloat16, 'x')
+    x, f16 = _half(x, 'x')
     N, H, W, Cc = x.shape
     with torch.cuda.device(x.device):
-        y = torch.empty((N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, Cc), dtype=torch.bfloat16, device=x.device)
-        _lib.check(lib.nbc_maxpool3x3s2_bf16(_ptr(x), N, H, W, Cc, _ptr(y), _stream(x.device)), 'nbc_maxpool3x3s2_bf16')
+        y = torch.empty((N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, Cc), dtype=x.dtype, device=x.device)
+        _lib.check(lib.nbc_maxpool3x3s2_bf16(_ptr(x), N, H, W, Cc, f16, _ptr(y), _stream(x.device)), 'nbc_maxpool3x3s2_bf16')
     return y
 
 
 def head_1x1(x, weight, bias):
-    """x bf16 NHWC [N,h,w,Cin], weight f32 [3,Cin], bias f32[3] -> f32 [N,3,h,w]."""
+    """x bf16|fp16 NHWC [N,h,w,Cin], weight f32 [3,Cin], bias f32[3] -> f32 [N,3,h,w]."""
     lib = _lib.load()
-    x = _contig(x, torch.bfloat16, 'x')
+    x, f16 = _half(x, 'x')
     N, h, w, Cin = x.shape
     with torch.cuda.device(x.device):
         out = torch.empty((N, 3, h, w), dtype=torch.float32, device=x.device)
-        _lib.check(lib.nbc_head_1x1(_ptr(x), h * w, N, Cin, _ptr(_contig(weight, torch.float32, 'weight')),
+        _lib.check(lib.nbc_head_1x1(_ptr(x), h * w, N, Cin, f16, _ptr(_contig(weight, torch.float32, 'weight')),
                                     _ptr(_contig(bias, torch.float32, 'bias')), _ptr(out), _stream(x.device)), 'nbc_head_1x1')
     return out
 
@@ -299,8 +312,11 @@ def wce_fwd_bwd(logits, target, weights, need_grad=True):
 class Plan:
     """Owns an nbc_plan (BN-folded bf16 weights on the device) built from the 326 state_dict tensors."""
 
-    def __init__(self, tensors, mean, std, device):
+    def __init__(self, tensors, mean, std, device, precision='bf16'):
         lib = _lib.load()
+        if precision not in HALF_DTYPES:
+            raise ValueError("precision must be 'bf16' or 'fp16'")
+        self.precision = precision
         self.device = torch.device(device)
         _lib.require_device(self.device.index if self.device.index is not None else torch.cuda.current_device())
         keep = []
@@ -312,7 +328,7 @@ class Plan:
         s3 = (C.c_float * 3)(*std)
         with torch.cuda.device(self.device):
             torch.cuda.current_stream().synchronize()
-            self.handle = lib.nbc_plan_create(arr, len(keep), m3, s3)
+            self.handle = lib.nbc_plan_create(arr, len(keep), m3, s3, 1 if precision == 'fp16' else 0)
         if not self.handle:
             raise RuntimeError('nbc_plan_create failed: ' + _lib.last_error())
         self._ws = None

@@ -99,20 +99,20 @@ CONV_SHAPES = [(64, 64, 1, 1, 1), (64, 64, 3, 1, 1), (64, 256, 1, 1, 1), (256, 6
                (1024, 2048, 1, 1, 1), (2048, 512, 1, 1, 1), (2048, 512, 3, 1, 1)]
 
 
-def _conv_case(dev, Cin, Cout, k, stride, dil, N, H, W, relu, use_res, impl, seed=0):
+def _conv_case(dev, Cin, Cout, k, stride, dil, N, H, W, relu, use_res, impl, seed=0, dtype=torch.bfloat16):
     ops = _ops()
     g = torch.Generator().manual_seed(seed)
-    x = torch.randn(N, H, W, Cin, generator=g).to(torch.bfloat16)
+    x = torch.randn(N, H, W, Cin, generator=g).to(dtype)
     w = (torch.randn(Cout, Cin, k, k, generator=g) / np.sqrt(Cin * k * k)).to(torch.float32)
     gamma = torch.rand(Cout, generator=g) + 0.5
     beta = torch.randn(Cout, generator=g) * 0.1
     mean = torch.randn(Cout, generator=g) * 0.1
     var = torch.rand(Cout, generator=g) + 0.5
     pad = dil if k == 3 else 0
-    wp, bias = ops.fold_bn_pack(w.to(dev), (gamma.to(dev), beta.to(dev), mean.to(dev), var.to(dev)))
+    wp, bias = ops.fold_bn_pack(w.to(dev), (gamma.to(dev), beta.to(dev), mean.to(dev), var.to(dev)), dtype=dtype)
     Ho = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
     Wo = (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
-    res = torch.randn(N, Ho, Wo, Cout, generator=g).to(torch.bfloat16) if use_res else None
+    res = torch.randn(N, Ho, Wo, Cout, generator=g).to(dtype) if use_res else None
     y = ops.conv_bf16(x.to(dev), wp, bias, stride=stride, pad=pad, dil=dil, relu=relu,
                       residual=res.to(dev) if use_res else None, impl=impl)
     torch.cuda.synchronize()
@@ -127,7 +127,8 @@ def _conv_case(dev, Cin, Cout, k, stride, dil, N, H, W, relu, use_res, impl, see
     got = y.float().cpu()
     assert got.shape == ref.shape
     err = (got - ref).abs()
-    tol = 2.0 ** -7 * ref.abs() + 2e-2      # bf16 output rounding (2^-8 rel) + f32 accumulation-order slack
+    # output rounding (bf16: 2^-8 rel, fp16: 2^-11 rel) + f32 accumulation-order slack
+    tol = (2.0 ** -7 * ref.abs() + 2e-2) if dtype == torch.bfloat16 else (2.0 ** -10 * ref.abs() + 2e-3)
     bad = (err > tol)
     assert not bad.any(), 'max err %.4g at %s (ref %.4g) bad=%d' % (err.max(), np.unravel_index(err.argmax(), err.shape),
                                                                    ref.flatten()[err.argmax()], int(bad.sum()))
@@ -152,6 +153,14 @@ def test_conv_full_width_rows(cuda_device, impl):
     _conv_case(cuda_device, 512, 512, 3, 1, 4, N=1, H=16, W=128, relu=False, use_res=False, impl=impl, seed=2)
     _conv_case(cuda_device, 128, 128, 3, 2, 1, N=1, H=33, W=255, relu=True, use_res=False, impl=impl, seed=3)
     _conv_case(cuda_device, 256, 512, 1, 2, 1, N=2, H=31, W=256, relu=False, use_res=False, impl=impl, seed=4)
+
+
+@pytest.mark.parametrize('impl', IMPLS)
+def test_conv_fp16_storage(cuda_device, impl):
+    # fp16 operands / outputs (precision='fp16'): same kernels, tighter tolerance
+    for (Cin, Cout, k, stride, dil) in [(64, 256, 1, 1, 1), (128, 128, 3, 2, 1), (512, 512, 3, 1, 4), (2048, 512, 3, 1, 1)]:
+        _conv_case(cuda_device, Cin, Cout, k, stride, dil, N=2, H=27, W=40, relu=True, use_res=(k == 1), impl=impl,
+                   dtype=torch.float16)
 
 
 def test_conv_tc_many_tiles(cuda_device):
@@ -187,6 +196,11 @@ def test_stem_maxpool_head(cuda_device):
         gt = yt.float().cpu().permute(0, 3, 1, 2)
         assert gt.shape == ref.shape
         assert (gt - ref).abs().max() < 0.02 * ref.abs().max() + 1e-2, (gt - ref).abs().max()
+    yh = ops.stem_tc(x.to(dev), omodel.DEFAULT_MEAN, omodel.DEFAULT_STD, wf, bf, dtype=torch.float16)
+    assert yh.dtype == torch.float16
+    assert (yh.float().cpu().permute(0, 3, 1, 2) - ref).abs().max() < 0.003 * ref.abs().max() + 2e-3
+    ph = ops.maxpool3x3s2(yh)
+    assert torch.equal(ph.float().cpu().permute(0, 3, 1, 2), torch.nn.functional.max_pool2d(yh.float().cpu().permute(0, 3, 1, 2), 3, 2, 1))
     big = np.stack([synth.texture_u8(203, 517, 5), synth.texture_u8(203, 517, 6)])
     yb = ops.stem_tc(torch.from_numpy(big).to(dev), omodel.DEFAULT_MEAN, omodel.DEFAULT_STD, wf, bf).float().cpu()
     for i in range(2):
