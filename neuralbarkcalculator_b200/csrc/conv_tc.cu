@@ -60,7 +60,9 @@ struct TcCfg {
   static constexpr uint32_t kSwizzleBytes = KBLK * 2;  // 128 or 64
 };
 
-template <int BN, int KBLK>
+// RES / RELU / F16 are compile-time so the epilogue inner loop carries no runtime branches: on the low-K layers the
+// epilogue's instruction count per output element, not the MMA, sets the pace.
+template <int BN, int KBLK, bool RES, bool RELU, bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   using Cfg = TcCfg<BN, KBLK>;
   constexpr int kABytes = Cfg::kABytes;
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     if (elect_one()) {
-      const uint32_t idesc = p.f16 ? umma_idesc_f16(128, BN) : umma_idesc_bf16(128, BN);
+      constexpr uint32_t idesc = F16 ? umma_idesc_f16(128, BN) : umma_idesc_bf16(128, BN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         if (p.valid_h != nullptr) {
@@ -189,7 +191,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       const int th_i = m_tile % p.tiles_h;
       const int img = m_tile / p.tiles_h;
       const int n0 = n_tile * BN + half * kCols;
-      int64_t offs[2];
+      __nv_bfloat16* optr[2];          // this lane's two output rows of the tile, at its 8-column piece
+      const __nv_bfloat16* rptr[2];
       bool ok[2];     // this row is stored
       bool live[2];   // ... with computed values (otherwise zeros: the halo rows of a ragged batch)
       const int vh = p.valid_h != nullptr ? __ldg(p.valid_h + img) : INT_MAX;
@@ -200,7 +203,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         const int w = (tw_i << p.tw_log2) + (row & (p.tw - 1)), h = th_i * p.th + (row >> p.tw_log2);
         ok[j] = (w < p.Wo) && (h < p.Ho) && (h < vz);
         live[j] = h < vh;
-        offs[j] = (((int64_t)img * p.Ho + h) * p.Wo + w) * p.Cout + n0 + cpiece * 8;
+        const int64_t off = (((int64_t)img * p.Ho + h) * p.Wo + w) * p.Cout + n0 + cpiece * 8;
+        optr[j] = p.out + off;
+        rptr[j] = RES ? p.residual + off : nullptr;
       }
       if (th_i * p.th >= vh) {
         // dead tile: no MMA was issued for it; only the zero halo is written
@@ -208,35 +213,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           for (int c = 0; c < kCols; c += 16)
 #pragma unroll
             for (int j = 0; j < 2; ++j)
-              if (ok[j]) *reinterpret_cast<uint4*>(p.out + offs[j] + c) = make_uint4(0u, 0u, 0u, 0u);
+              if (ok[j]) *reinterpret_cast<uint4*>(optr[j] + c) = make_uint4(0u, 0u, 0u, 0u);
         }
         continue;
       }
-      const bool has_res = p.residual != nullptr;
+      const bool st0 = ok[0], st1 = ok[1];
+      const bool lv0 = ok[0] && live[0], lv1 = ok[1] && live[1];
       uint4 res_nxt[2];
-      if (has_res) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-          if (ok[j] && live[j]) res_nxt[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + offs[j]));
+      if (RES) {
+        if (lv0) res_nxt[0] = __ldg(reinterpret_cast<const uint4*>(rptr[0]));
+        if (lv1) res_nxt[1] = __ldg(reinterpret_cast<const uint4*>(rptr[1]));
       }
       mbar_wait(&tfull_bar[acc], acc_phase, 400 + (int)acc);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * kCols;
+      const float* bias_p = p.bias + n0 + cpiece * 8;
+      float4* const wr = reinterpret_cast<float4*>(stg + lane * 20);
+      const float4* const rd0 = reinterpret_cast<const float4*>(stg + crow * 20 + cpiece * 8);
+      const float4* const rd1 = reinterpret_cast<const float4*>(stg + (crow + 16) * 20 + cpiece * 8);
 #pragma unroll 2
       for (int c = 0; c < kCols; c += 16) {
         uint32_t r[16];
         tmem_ld16(t_row + c, r);
         uint4 res[2];
-        res[0] = res_nxt[0], res[1] = res_nxt[1];
-        if (has_res && c + 16 < kCols) {
-#pragma unroll
-          for (int j = 0; j < 2; ++j)
-            if (ok[j] && live[j]) res_nxt[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + offs[j] + c + 16));
+        if (RES) {
+          res[0] = res_nxt[0], res[1] = res_nxt[1];
+          if (c + 16 < kCols) {
+            if (lv0) res_nxt[0] = __ldg(reinterpret_cast<const uint4*>(rptr[0] + c + 16));
+            if (lv1) res_nxt[1] = __ldg(reinterpret_cast<const uint4*>(rptr[1] + c + 16));
+          }
         }
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + cpiece * 8));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + cpiece * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias_p + c));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias_p + c + 4));
         tmem_ld_wait();
-        float4* wr = reinterpret_cast<float4*>(stg + lane * 20);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           wr[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
@@ -244,24 +253,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const float4* rd = reinterpret_cast<const float4*>(stg + (crow + 16 * j) * 20 + cpiece * 8);
+          const float4* rd = j == 0 ? rd0 : rd1;
           const float4 v0 = rd[0], v1 = rd[1];
           float v[8] = {v0.x + b0.x, v0.y + b0.y, v0.z + b0.z, v0.w + b0.w, v1.x + b1.x, v1.y + b1.y, v1.z + b1.z, v1.w + b1.w};
-          if (ok[j]) {
-            if (has_res && live[j]) {
-              const uint32_t rv[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
+          if (RES) {
+            const uint32_t rv[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
 #pragma unroll
-              for (int k = 0; k < 4; ++k) v[2 * k] += lo16(rv[k], p.f16), v[2 * k + 1] += hi16(rv[k], p.f16);
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
-            }
-            *reinterpret_cast<uint4*>(p.out + offs[j] + c) =
-                live[j] ? make_uint4(pack16x2(v[0], v[1], p.f16), pack16x2(v[2], v[3], p.f16), pack16x2(v[4], v[5], p.f16),
-                                     pack16x2(v[6], v[7], p.f16))
-                        : make_uint4(0u, 0u, 0u, 0u);
+            for (int k = 0; k < 4; ++k) v[2 * k] += lo16(rv[k], F16), v[2 * k + 1] += hi16(rv[k], F16);
           }
+          if (RELU) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+          }
+          uint4 o = make_uint4(pack16x2(v[0], v[1], F16), pack16x2(v[2], v[3], F16), pack16x2(v[4], v[5], F16),
+                               pack16x2(v[6], v[7], F16));
+          const bool lv = j == 0 ? lv0 : lv1;
+          if (!lv) o = make_uint4(0u, 0u, 0u, 0u);     // halo row of a ragged batch (or garbage from a dead residual)
+          if (j == 0 ? st0 : st1) *reinterpret_cast<uint4*>(optr[j] + c) = o;
         }
         __syncwarp();
       }
@@ -425,17 +433,32 @@ static int build_launch(const ConvGeom& g, const void* x, const void* w, const f
   return 0;
 }
 
-template <int BN, int KBLK>
-static int launch_bn(const ConvTcLaunch& L, cudaStream_t stream) {
+template <int BN, int KBLK, bool RES, bool RELU, bool F16>
+static int launch_one(const ConvTcLaunch& L, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    NBC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NBC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KBLK, RES, RELU, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   TcCfg<BN, KBLK>::kSmemBytes));
     attr_set = true;
   }
-  conv_tc_kernel<BN, KBLK><<<L.grid, kTcThreads, TcCfg<BN, KBLK>::kSmemBytes, stream>>>(L.p);
+  conv_tc_kernel<BN, KBLK, RES, RELU, F16><<<L.grid, kTcThreads, TcCfg<BN, KBLK>::kSmemBytes, stream>>>(L.p);
   NBC_CHECK_LAUNCH();
   return 0;
+}
+
+template <int BN, int KBLK>
+static int launch_bn(const ConvTcLaunch& L, cudaStream_t stream) {
+  const int key = (L.p.residual != nullptr ? 4 : 0) | (L.p.relu ? 2 : 0) | (L.p.f16 ? 1 : 0);
+  switch (key) {
+    case 0: return launch_one<BN, KBLK, false, false, false>(L, stream);
+    case 1: return launch_one<BN, KBLK, false, false, true>(L, stream);
+    case 2: return launch_one<BN, KBLK, false, true, false>(L, stream);
+    case 3: return launch_one<BN, KBLK, false, true, true>(L, stream);
+    case 4: return launch_one<BN, KBLK, true, false, false>(L, stream);
+    case 5: return launch_one<BN, KBLK, true, false, true>(L, stream);
+    case 6: return launch_one<BN, KBLK, true, true, false>(L, stream);
+    default: return launch_one<BN, KBLK, true, true, true>(L, stream);
+  }
 }
 
 // Stem as an implicit GEMM (see stem.cu): A = the zero-padded, normalised bf16 image [N][Hp][Wp][4]; one K block is
