@@ -53,7 +53,8 @@ struct TcCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int kStagingBytes = 8 * 32 * 20 * 4;  // epilogue transpose tiles: 8 warps x 32 rows x 20 words
+  // epilogue transpose tiles (8 warps x 32 rows x 20 words) + per-warp bias slices (8 x BN/2 floats)
+  static constexpr int kStagingBytes = 8 * 32 * 20 * 4 + 8 * (BN / 2) * 4;
   static constexpr int kUsedBytes = kStages * kStageBytes + 1024 /*barriers*/ + kStagingBytes + 1024 /*align slack*/;
   // > half an SM's shared memory keeps one CTA (one TMEM owner) per SM
   static constexpr int kSmemBytes = kUsedBytes < 120 * 1024 ? 120 * 1024 : kUsedBytes;
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     const int half = ew >> 2;        // which half of the BN columns
     constexpr int kCols = BN / 2;    // columns per warp
     float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 1024) + ew * (32 * 20);
+    float* sbias = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 1024 + 8 * 32 * 20 * 4) + ew * kCols;
     const int crow = lane >> 1, cpiece = lane & 1;
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -219,32 +221,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       }
       const bool st0 = ok[0], st1 = ok[1];
       const bool lv0 = ok[0] && live[0], lv1 = ok[1] && live[1];
-      uint4 res_nxt[2];
+      // All global loads of the tile are issued BEFORE waiting for the accumulator, so their latency hides behind
+      // the MMA main loop: the whole residual tile sits in registers (2 x 16 B per 16-column chunk per lane), the
+      // bias slice of this warp goes to its private smem row.
+      constexpr int kChunks = kCols / 16;
+      uint4 res[kChunks][2];
       if (RES) {
-        if (lv0) res_nxt[0] = __ldg(reinterpret_cast<const uint4*>(rptr[0]));
-        if (lv1) res_nxt[1] = __ldg(reinterpret_cast<const uint4*>(rptr[1]));
+#pragma unroll
+        for (int ci = 0; ci < kChunks; ++ci) {
+          if (lv0) res[ci][0] = __ldg(reinterpret_cast<const uint4*>(rptr[0] + ci * 16));
+          if (lv1) res[ci][1] = __ldg(reinterpret_cast<const uint4*>(rptr[1] + ci * 16));
+        }
       }
+      __syncwarp();   // previous tile's readers of sbias are done
+      for (int i = lane; i < kCols; i += 32) sbias[i] = __ldg(p.bias + n0 + i);
+      __syncwarp();
       mbar_wait(&tfull_bar[acc], acc_phase, 400 + (int)acc);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * kCols;
-      const float* bias_p = p.bias + n0 + cpiece * 8;
       float4* const wr = reinterpret_cast<float4*>(stg + lane * 20);
       const float4* const rd0 = reinterpret_cast<const float4*>(stg + crow * 20 + cpiece * 8);
       const float4* const rd1 = reinterpret_cast<const float4*>(stg + (crow + 16) * 20 + cpiece * 8);
-#pragma unroll 2
-      for (int c = 0; c < kCols; c += 16) {
+#pragma unroll
+      for (int ci = 0; ci < kChunks; ++ci) {
+        const int c = ci * 16;
         uint32_t r[16];
         tmem_ld16(t_row + c, r);
-        uint4 res[2];
-        if (RES) {
-          res[0] = res_nxt[0], res[1] = res_nxt[1];
-          if (c + 16 < kCols) {
-            if (lv0) res_nxt[0] = __ldg(reinterpret_cast<const uint4*>(rptr[0] + c + 16));
-            if (lv1) res_nxt[1] = __ldg(reinterpret_cast<const uint4*>(rptr[1] + c + 16));
-          }
-        }
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias_p + c));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias_p + c + 4));
+        const float4 b0 = *reinterpret_cast<const float4*>(sbias + c + cpiece * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(sbias + c + cpiece * 8 + 4);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           const float4 v0 = rd[0], v1 = rd[1];
           float v[8] = {v0.x + b0.x, v0.y + b0.y, v0.z + b0.z, v0.w + b0.w, v1.x + b1.x, v1.y + b1.y, v1.z + b1.z, v1.w + b1.w};
           if (RES) {
-            const uint32_t rv[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
+            const uint32_t rv[4] = {res[ci][j].x, res[ci][j].y, res[ci][j].z, res[ci][j].w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) v[2 * k] += lo16(rv[k], F16), v[2 * k + 1] += hi16(rv[k], F16);
           }
