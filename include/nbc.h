@@ -160,6 +160,33 @@ int nbc_plan_profile(nbc_plan* plan, const void* input, int input_kind, int N, i
 /* conv implementation used by the plan: 0 auto, 1 force tcgen05 where legal, 2 force mma.sync */
 int nbc_plan_set_impl(nbc_plan* plan, int impl);
 
+/* ---- training step  (__main__.py:231-269: train-mode forward, loss, backward, Adam; utils.py:151-165 as the loss) ----
+ * A plan is built for a fixed (N, H, W).  All state is caller-allocated and flat:
+ *   params / grads / adam_m / adam_v : f32[nbc_train_param_count]   (conv weights in [Cout][kh][kw][Cin] order)
+ *   stats                            : f32[nbc_train_stats_count]   (BatchNorm running mean / var)
+ * nbc_train_exchange converts between the 326 state_dict tensors (torchvision order, OIHW) and the flat buffers:
+ * direction 0 loads tensors -> (params, stats), 1 stores (params, stats) -> tensors.  Storing the gradient buffer
+ * gives per-layer gradients in state_dict layout (stats = NULL).
+ * nbc_train_forward_backward: input_kind 0 = u8 NHWC images (normalised inside), 1 = f32 NCHW; target u8 [N,H,W];
+ * BatchNorm uses batch statistics and updates `stats` (momentum 0.1) unless stats is NULL; dropout_p applies to the
+ * head (mask = hash(seed, index)); loss = mean weighted CE (device scalar); grads are overwritten.
+ * Data-parallel training: all-reduce `grads` (sum) across ranks, then nbc_train_adam with grad_scale = 1/world.
+ * nbc_train_adam follows torch.optim.Adam (L2 weight decay added to the gradient, bias correction by `step` >= 1). */
+typedef struct nbc_train_plan nbc_train_plan;
+nbc_train_plan* nbc_train_create(int N, int H, int W);
+void nbc_train_destroy(nbc_train_plan* plan);
+int64_t nbc_train_param_count(const nbc_train_plan* plan);
+int64_t nbc_train_stats_count(const nbc_train_plan* plan);
+size_t nbc_train_workspace_bytes(const nbc_train_plan* plan);
+int nbc_train_exchange(nbc_train_plan* plan, void* const* tensors_host, int n_tensors, float* params, float* stats,
+                       int direction, void* stream);
+int nbc_train_forward_backward(nbc_train_plan* plan, float* params, float* stats, float* grads, const void* input,
+                               int input_kind, const float* mean3_host, const float* std3_host, const uint8_t* target,
+                               const float* weights3, float dropout_p, uint64_t seed, float* loss, void* workspace,
+                               size_t workspace_bytes, void* stream);
+int nbc_train_adam(float* params, const float* grads, float* adam_m, float* adam_v, int64_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,17 @@ SIGNATURES = {
     'nbc_plan_profile': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p,
                                  C.POINTER(c_float), C.POINTER(C.c_double), c_int]),
     'nbc_plan_set_impl': (c_int, [c_void_p, c_int]),
+    'nbc_train_create': (c_void_p, [c_int, c_int, c_int]),
+    'nbc_train_destroy': (None, [c_void_p]),
+    'nbc_train_param_count': (c_i64, [c_void_p]),
+    'nbc_train_stats_count': (c_i64, [c_void_p]),
+    'nbc_train_workspace_bytes': (c_size_t, [c_void_p]),
+    'nbc_train_exchange': (c_int, [c_void_p, C.POINTER(c_void_p), c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    'nbc_train_forward_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, C.POINTER(c_float),
+                                   C.POINTER(c_float), c_void_p, c_void_p, c_float, C.c_uint64, c_void_p, c_void_p, c_size_t,
+                                   c_void_p]),
+    'nbc_train_adam': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float, c_float,
+                       c_int, c_float, c_void_p]),
 }
 
 _lib = None

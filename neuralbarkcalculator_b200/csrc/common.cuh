@@ -47,8 +47,8 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
     }                                                                                        \
   } while (0)
 
-static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
-static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int sm_count();
 

@@ -28,7 +28,7 @@ int conv_tc_prepare(const ConvGeom& g, const void* x, const void* w, const float
 int conv_tc_run(const ConvTcPrepared* prep, cudaStream_t stream);
 // stem 7x7/2 as an implicit GEMM over the padded bf16 image (see stem.cu)
 int conv_tc_prepare_stem(int N, int Ho, int Wo, int Hp, int Wp, const void* padded, const void* w224, const float* bias,
-                         void* y, ConvTcPrepared* out, const int* valid_h = nullptr, int f16 = 0);
+                         void* y, ConvTcPrepared* out, const int* valid_h = nullptr, int f16 = 0, int relu = 1);
 int conv_tc(const ConvGeom& g, const void* x, const void* w, const float* bias, const void* residual, void* y,
             cudaStream_t stream);
 

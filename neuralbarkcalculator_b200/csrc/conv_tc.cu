@@ -183,7 +183,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     constexpr int kCols = BN / 2;    // columns per warp
     float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 1024) + ew * (32 * 20);
     float* sbias = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 1024 + 8 * 32 * 20 * 4) + ew * kCols;
-    const int crow = lane >> 1, cpiece = lane & 1;
+    // lane -> (row, 8-column piece) of the coalesced domain.  A quarter-warp (the unit the smem banks are resolved for
+    // 16-byte accesses) reads 8 different rows of the same piece: with the 20-word pitch that is conflict-free, and the
+    // global side still sees 16 rows x 32 contiguous bytes per instruction.
+    const int crow = (lane & 7) + ((lane >> 4) << 3), cpiece = (lane >> 3) & 1;
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.num_n_tiles;
@@ -470,7 +473,7 @@ static int launch_bn(const ConvTcLaunch& L, cudaStream_t stream) {
 // The windows of neighbouring outputs overlap (stride 16 B, extent 64 B): the tensor map simply describes that
 // address function.  Even / odd padded rows are two lattices, exactly like the stride-2 convolutions.
 int conv_tc_prepare_stem(int N, int Ho, int Wo, int Hp, int Wp, const void* padded, const void* w224, const float* bias,
-                         void* y, ConvTcPrepared* out, const int* valid_h, int f16) {
+                         void* y, ConvTcPrepared* out, const int* valid_h, int f16, int relu) {
   ConvTcLaunch* L = reinterpret_cast<ConvTcLaunch*>(out->storage);
   ConvTcParams& p = L->p;
   memset(&p, 0, sizeof(p));
@@ -479,7 +482,7 @@ int conv_tc_prepare_stem(int N, int Ho, int Wo, int Hp, int Wp, const void* padd
   p.N = N, p.Ho = Ho, p.Wo = Wo, p.Cout = 64;
   p.num_m_tiles = N * p.tiles_w * p.tiles_h;
   p.num_n_tiles = 1;
-  p.n_taps = 7, p.cblocks = 1, p.relu = 1;
+  p.n_taps = 7, p.cblocks = 1, p.relu = relu;
   p.bias = bias, p.residual = nullptr, p.out = reinterpret_cast<__nv_bfloat16*>(y);
   p.valid_h = valid_h;
   L->block_n = 64, L->kblk = 32;

@@ -1,0 +1,319 @@
+// Training-path kernels, part 2: maxpool backward, stem weight gradient, dropout, classifier (1x1) backward, the
+// adjoint of the bicubic upsample, zero insertion for stride-2 data gradients, and Adam.
+#include "common.cuh"
+#include "cubic.cuh"
+#include "train.h"
+
+namespace nbc {
+
+static int grid_for2(int64_t n) {
+  const int64_t b = ceil_div64(n, 256);
+  return (int)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
+}
+
+// ------------------------------------------------------------------------------------------------ maxpool backward
+// dx[n,h,w,c] = sum of dy over the (<= 4) 3x3/2 windows whose FIRST maximum (row-major scan, torch's rule) is (h,w).
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                          int N, int H, int W, int C, int Ho, int Wo,
+                                                          __nv_bfloat16* __restrict__ dx) {
+  const int64_t total = (int64_t)N * H * W * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t t = i / C;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    const __nv_bfloat16* xn = x + (int64_t)n * H * W * C + c;
+    const float v = __bfloat162float(xn[((int64_t)h * W + w) * C]);
+    float g = 0.f;
+    // windows (ho, wo) with 2*ho-1 <= h <= 2*ho+1
+    for (int ho = max(0, (h - 1 + 1) / 2); ho <= min(Ho - 1, (h + 1) / 2); ++ho) {
+      for (int wo = max(0, w / 2); wo <= min(Wo - 1, (w + 1) / 2); ++wo) {
+        // is (h, w) the first maximum of this window?
+        bool first = true;
+        for (int dy_ = -1; dy_ <= 1 && first; ++dy_) {
+          const int hh = 2 * ho + dy_;
+          if (hh < 0 || hh >= H) continue;
+          for (int dx_ = -1; dx_ <= 1; ++dx_) {
+            const int ww = 2 * wo + dx_;
+            if (ww < 0 || ww >= W) continue;
+            const float u = __bfloat162float(xn[((int64_t)hh * W + ww) * C]);
+            const bool before = (hh < h) || (hh == h && ww < w);
+            if (u > v || (before && u == v)) {
+              first = false;
+              break;
+            }
+          }
+        }
+        if (first) g += __bfloat162float(dy[(((int64_t)n * Ho + ho) * Wo + wo) * C + c]);
+      }
+    }
+    dx[i] = __float2bfloat16_rn(g);
+  }
+}
+
+int maxpool_backward(const void* x, const void* dy, int N, int H, int W, int C, void* dx, cudaStream_t stream) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  maxpool_bwd_kernel<<<grid_for2((int64_t)N * H * W * C), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), N, H, W, C, Ho, Wo,
+      reinterpret_cast<__nv_bfloat16*>(dx));
+  NBC_CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ stem weight gradient
+// dW[oc][ky][kx][c] += sum_p dz[p][oc] * padded[n][2ho+ky][2wo+kx][c]   (padded = the bf16 staging image of the stem)
+// block = 64 output pixels; thread (oc = tid & 63, g = tid >> 6) accumulates the taps t = g, g+4, ... (37 of 147)
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const __nv_bfloat16* __restrict__ dz, const uint2* __restrict__ padded,
+                                                         int N, int Ho, int Wo, int Hp, int Wp, float* __restrict__ dw) {
+  __shared__ float s_in[8][16][4];   // input patch rows ky..: 7 rows x (2*? ) -- one output pixel at a time (see below)
+  __shared__ float s_dz[64];
+  const int tid = threadIdx.x, oc = tid & 63, g = tid >> 6;
+  float acc[37];
+  int off[37];   // smem offset of tap tp = g + 4 i : ((ky * 16 + kx) * 4 + c)
+#pragma unroll
+  for (int i = 0; i < 37; ++i) {
+    acc[i] = 0.f;
+    const int tp = min(g + 4 * i, 146), c = tp % 3, kk = tp / 3;
+    off[i] = ((kk / 7) * 16 + (kk % 7)) * 4 + c;
+  }
+  const float* s_flat = &s_in[0][0][0];
+  const int64_t M = (int64_t)N * Ho * Wo;
+  const int64_t per_block = ceil_div64(M, gridDim.x);
+  const int64_t m0 = (int64_t)blockIdx.x * per_block, m1 = min(M, m0 + per_block);
+  for (int64_t m = m0; m < m1; ++m) {
+    const int wo = (int)(m % Wo);
+    const int64_t t = m / Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    __syncthreads();
+    if (tid < 64) s_dz[tid] = __bfloat162float(dz[m * 64 + tid]);
+    if (tid >= 64 && tid < 64 + 56) {   // 7 rows x 8 pixels of the padded image (the 8th pixel is never used)
+      const int k = tid - 64, ky = k >> 3, kx = k & 7;
+      const uint2 v = __ldg(padded + ((int64_t)n * Hp + 2 * ho + ky) * Wp + 2 * wo + kx);
+      s_in[ky][kx][0] = bf16lo(v.x), s_in[ky][kx][1] = bf16hi(v.x), s_in[ky][kx][2] = bf16lo(v.y), s_in[ky][kx][3] = 0.f;
+    }
+    __syncthreads();
+    const float d = s_dz[oc];
+#pragma unroll
+    for (int i = 0; i < 37; ++i) acc[i] = fmaf(d, s_flat[off[i]], acc[i]);   // tap index (ky*7 + kx)*3 + c
+  }
+#pragma unroll
+  for (int i = 0; i < 37; ++i) {
+    const int tp = g + 4 * i;
+    if (tp < 147) atomicAdd(dw + oc * 147 + tp, acc[i]);
+  }
+}
+
+int stem_wgrad(const void* dz, const void* padded, int N, int Ho, int Wo, float* dw, cudaStream_t stream) {
+  stem_wgrad_kernel<<<148 * 8, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dz),
+                                                 reinterpret_cast<const uint2*>(padded), N, Ho, Wo, 2 * Ho + 5, 2 * Wo + 6, dw);
+  NBC_CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ dropout
+// keep(i) = hash(seed, i) >= p, scaled by 1/(1-p); the same hash gives the backward mask, nothing is stored
+__device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t i) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (i + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+__global__ void __launch_bounds__(256) dropout_kernel(const __nv_bfloat16* __restrict__ x, int64_t n, float p, uint64_t seed,
+                                                      __nv_bfloat16* __restrict__ y) {
+  const float scale = 1.f / (1.f - p);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = __bfloat162float(x[i]);
+    y[i] = __float2bfloat16_rn(hash_uniform(seed, (uint64_t)i) >= p ? v * scale : 0.f);
+  }
+}
+int dropout_apply(const void* x, int64_t n, float p, uint64_t seed, void* y, cudaStream_t stream) {
+  dropout_kernel<<<grid_for2(n), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, p, seed,
+                                                   reinterpret_cast<__nv_bfloat16*>(y));
+  NBC_CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ classifier backward
+// dlow f32 [N][3][P];  x bf16 [N*P][C] (after dropout);  w f32 [3][C]
+// dx[p][k] = sum_c dlow[c][p] * w[c][k]  (then through the dropout mask);  dW[c][k] += sum_p dlow[c][p] x[p][k]; db[c] += sum_p
+__global__ void __launch_bounds__(256) cls_bwd_kernel(const float* __restrict__ dlow, const __nv_bfloat16* __restrict__ x,
+                                                      const float* __restrict__ w, int N, int64_t P, int C, float drop_p,
+                                                      uint64_t seed, __nv_bfloat16* __restrict__ dx, float* __restrict__ dw,
+                                                      float* __restrict__ db) {
+  // thread owns channels k = tid, tid + 256, ...; block owns a slab of pixels
+  const int64_t M = (int64_t)N * P;
+  const int64_t per_block = ceil_div64(M, gridDim.x);
+  const int64_t m0 = (int64_t)blockIdx.x * per_block, m1 = min(M, m0 + per_block);
+  const float scale = 1.f / (1.f - drop_p);
+  for (int k = threadIdx.x; k < C; k += blockDim.x) {
+    const float w0 = w[k], w1 = w[C + k], w2 = w[2 * C + k];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int64_t m = m0; m < m1; ++m) {
+      const int64_t n = m / P, pix = m - n * P;
+      const float* d = dlow + n * 3 * P + pix;
+      const float d0 = __ldg(d), d1 = __ldg(d + P), d2 = __ldg(d + 2 * P);
+      const float xv = __bfloat162float(x[m * C + k]);
+      a0 = fmaf(d0, xv, a0), a1 = fmaf(d1, xv, a1), a2 = fmaf(d2, xv, a2);
+      float g = d0 * w0 + d1 * w1 + d2 * w2;
+      if (drop_p > 0.f) g = hash_uniform(seed, (uint64_t)(m * C + k)) >= drop_p ? g * scale : 0.f;
+      dx[m * C + k] = __float2bfloat16_rn(g);
+    }
+    atomicAdd(dw + k, a0), atomicAdd(dw + C + k, a1), atomicAdd(dw + 2 * C + k, a2);
+  }
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+    for (int64_t m = m0; m < m1; ++m) {
+      const int64_t n = m / P, pix = m - n * P;
+      s += dlow[n * 3 * P + threadIdx.x * P + pix];
+    }
+    atomicAdd(db + threadIdx.x, s);
+  }
+}
+int cls_backward(const float* dlow, const void* x, const float* w, int N, int64_t P, int C, float drop_p, uint64_t seed,
+                 void* dx, float* dw, float* db, cudaStream_t stream) {
+  cls_bwd_kernel<<<148 * 4, 256, 0, stream>>>(dlow, reinterpret_cast<const __nv_bfloat16*>(x), w, N, P, C, drop_p, seed,
+                                              reinterpret_cast<__nv_bfloat16*>(dx), dw, db);
+  NBC_CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ upsample backward
+// adjoint of F.interpolate(mode='bicubic', align_corners=False): dlow[n,c,i,j] = sum_{Y,X} wy(Y,i) wx(X,j) dup[n,c,Y,X],
+// separable: first over X (-> T[n,c,Y,j]), then over Y.  taps tables idx/wt: [out][4]
+__global__ void taps_table_kernel(int in_size, int out_size, float scale, int* __restrict__ idx, float* __restrict__ wt) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= out_size) return;
+  int ix[4];
+  float w[4];
+  cubic_taps(d, scale, in_size, ix, w);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) idx[4 * d + k] = ix[k], wt[4 * d + k] = w[k];
+}
+// out[r][j] = sum over candidates d of w(d,j) * in[r][d] along the LAST dim (rows = everything else)
+__global__ void __launch_bounds__(256) adjoint_last_kernel(const float* __restrict__ in, int64_t rows, int out_size /*hi-res*/,
+                                                           int in_size /*lo-res*/, float inv_scale, const int* __restrict__ idx,
+                                                           const float* __restrict__ wt, float* __restrict__ out) {
+  const int64_t total = rows * in_size;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % in_size);
+    const int64_t r = i / in_size;
+    int lo = (int)floorf(((float)j - 2.5f) * inv_scale) - 2, hi = (int)ceilf(((float)j + 2.5f) * inv_scale) + 2;
+    if (j == 0) lo = 0;
+    if (j == in_size - 1) hi = out_size - 1;
+    lo = max(lo, 0), hi = min(hi, out_size - 1);
+    const float* src = in + r * out_size;
+    float acc = 0.f;
+    for (int d = lo; d <= hi; ++d) {
+      const float v = __ldg(src + d);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (__ldg(idx + 4 * d + k) == j) acc = fmaf(__ldg(wt + 4 * d + k), v, acc);
+    }
+    out[i] = acc;
+  }
+}
+// same along the second-to-last dim: in [R][H][w] -> out [R][h][w]
+__global__ void __launch_bounds__(256) adjoint_rows_kernel(const float* __restrict__ in, int64_t R, int H, int h, int w,
+                                                           float inv_scale, const int* __restrict__ idx,
+                                                           const float* __restrict__ wt, float* __restrict__ out) {
+  const int64_t total = R * h * w;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    int64_t t = i / w;
+    const int j = (int)(t % h);
+    const int64_t r = t / h;
+    int lo = (int)floorf(((float)j - 2.5f) * inv_scale) - 2, hi = (int)ceilf(((float)j + 2.5f) * inv_scale) + 2;
+    if (j == 0) lo = 0;
+    if (j == h - 1) hi = H - 1;
+    lo = max(lo, 0), hi = min(hi, H - 1);
+    const float* src = in + r * H * w + x;
+    float acc = 0.f;
+    for (int d = lo; d <= hi; ++d) {
+      const float v = __ldg(src + (int64_t)d * w);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (__ldg(idx + 4 * d + k) == j) acc = fmaf(__ldg(wt + 4 * d + k), v, acc);
+    }
+    out[i] = acc;
+  }
+}
+size_t upsample_bwd_workspace_bytes(int N, int C, int h, int w, int H, int W) {
+  return align_up((size_t)N * C * H * w * 4, 256) + align_up((size_t)(H + W) * 4 * 8, 256);
+}
+int upsample_backward(const float* dup, int N, int C, int h, int w, int H, int W, float* dlow, void* workspace,
+                      cudaStream_t stream) {
+  char* ws = reinterpret_cast<char*>(workspace);
+  float* T = reinterpret_cast<float*>(ws);
+  char* tb = ws + align_up((size_t)N * C * H * w * 4, 256);
+  int* idx_x = reinterpret_cast<int*>(tb);
+  float* wt_x = reinterpret_cast<float*>(tb + (size_t)W * 16);
+  int* idx_y = reinterpret_cast<int*>(tb + (size_t)W * 32);
+  float* wt_y = reinterpret_cast<float*>(tb + (size_t)W * 32 + (size_t)H * 16);
+  const float sx = (float)w / (float)W, sy = (float)h / (float)H;
+  taps_table_kernel<<<ceil_div(W, 128), 128, 0, stream>>>(w, W, sx, idx_x, wt_x);
+  NBC_CHECK_LAUNCH();
+  taps_table_kernel<<<ceil_div(H, 128), 128, 0, stream>>>(h, H, sy, idx_y, wt_y);
+  NBC_CHECK_LAUNCH();
+  adjoint_last_kernel<<<grid_for2((int64_t)N * C * H * w), 256, 0, stream>>>(dup, (int64_t)N * C * H, W, w, (float)W / (float)w,
+                                                                           idx_x, wt_x, T);
+  NBC_CHECK_LAUNCH();
+  adjoint_rows_kernel<<<grid_for2((int64_t)N * C * h * w), 256, 0, stream>>>(T, (int64_t)N * C, H, h, w, (float)H / (float)h,
+                                                                           idx_y, wt_y, dlow);
+  NBC_CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ zero insertion
+// up[n, 2h, 2w, :] = dz[n, h, w, :], zero elsewhere  (data gradient of a stride-2 conv = stride-1 conv of this)
+__global__ void __launch_bounds__(256) zero_insert_kernel(const uint4* __restrict__ dz, int N, int Ho, int Wo, int H, int W, int C8,
+                                                          uint4* __restrict__ up) {
+  const int64_t total = (int64_t)N * H * W * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    int64_t t = i / C8;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if ((h & 1) == 0 && (w & 1) == 0 && (h >> 1) < Ho && (w >> 1) < Wo)
+      v = __ldg(dz + (((int64_t)n * Ho + (h >> 1)) * Wo + (w >> 1)) * C8 + c);
+    up[i] = v;
+  }
+}
+int zero_insert(const void* dz, int N, int Ho, int Wo, int H, int W, int C, void* up, cudaStream_t stream) {
+  zero_insert_kernel<<<grid_for2((int64_t)N * H * W * (C / 8)), 256, 0, stream>>>(reinterpret_cast<const uint4*>(dz), N, Ho, Wo,
+                                                                               H, W, C / 8, reinterpret_cast<uint4*>(up));
+  NBC_CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ Adam
+// torch.optim.Adam (amsgrad=False, L2 weight decay added to the gradient), one fused pass over the flat buffers
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                                                   float wd, float bc1, float bc2_sqrt, float grad_scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * grad_scale;
+    const float pi = p[i];
+    gi = fmaf(wd, pi, gi);
+    const float mi = m[i] + (1.f - b1) * (gi - m[i]);          // lerp, as torch
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi, v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+int adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float wd,
+              int step, float grad_scale, cudaStream_t stream) {
+  const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
+  adam_kernel<<<grid_for2(n), 256, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, sqrtf(bc2), grad_scale);
+  NBC_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace nbc

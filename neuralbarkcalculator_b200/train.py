@@ -1,0 +1,147 @@
+"""Training step of the reference's ``__main__.py:231-269`` on the B200 path (row a14).
+
+``Trainer`` owns the flat parameter / gradient / Adam buffers (torch tensors = device memory only) and drives the native
+step in ``libnbc.so``: train-mode forward (batch-statistics BatchNorm, Dropout(0.8) in the head as
+``fcn_resnet50(dropout=0.8)``), ``CustomWeightedCrossEntropy`` (utils.py:151-165), full backward, and Adam
+(lr 5e-4, L2 weight decay 2e-3 as ``__main__.py:234``).  Data parallel: one process per GPU, the flat gradient buffer is
+all-reduced over NCCL (``torch.distributed``) between backward and the optimiser -- the only collective of the path.
+No torch autograd, no torch ops on the data path."""
+import ctypes as C
+
+import torch
+
+from . import _lib, ops
+from .utils import get_pos_weight
+
+
+class Trainer:
+    def __init__(self, state_dict, N, H, W, device='cuda:0', lr=5e-4, weight_decay=2e-3, betas=(0.9, 0.999), eps=1e-8,
+                 dropout=0.8, class_weights=None, mean=(0.7399, 0.6139, 0.4401), std=(0.1068, 0.1272, 0.1271)):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        _lib.require_device(self.device.index if self.device.index is not None else torch.cuda.current_device())
+        self.N, self.H, self.W = N, H, W
+        self.lr, self.wd, self.betas, self.eps, self.dropout = lr, weight_decay, betas, eps, dropout
+        self.mean3 = (C.c_float * 3)(*mean)
+        self.std3 = (C.c_float * 3)(*std)
+        self.step_count = 0
+        self.keys = list(state_dict.keys())
+        if len(self.keys) != 326:
+            raise RuntimeError('Trainer expects the 326-key fcn_resnet50 state_dict')
+        with torch.cuda.device(self.device):
+            self.handle = self.lib.nbc_train_create(N, H, W)
+            if not self.handle:
+                raise RuntimeError('nbc_train_create failed: ' + _lib.last_error())
+            h = C.c_void_p(self.handle)
+            n = self.lib.nbc_train_param_count(h)
+            self.params = torch.zeros(n, dtype=torch.float32, device=self.device)
+            self.grads = torch.zeros(n, dtype=torch.float32, device=self.device)
+            self.adam_m = torch.zeros(n, dtype=torch.float32, device=self.device)
+            self.adam_v = torch.zeros(n, dtype=torch.float32, device=self.device)
+            self.stats = torch.zeros(self.lib.nbc_train_stats_count(h), dtype=torch.float32, device=self.device)
+            self.ws = torch.empty(self.lib.nbc_train_workspace_bytes(h) + 1024, dtype=torch.uint8, device=self.device)
+            self.loss = torch.zeros((), dtype=torch.float32, device=self.device)
+            w = get_pos_weight() if class_weights is None else class_weights
+            self.class_weights = w.to(device=self.device, dtype=torch.float32).contiguous()
+            self._exchange(self._device_tensors(state_dict), self.params, self.stats, 0)
+        self.num_batches_tracked = {k: int(v) for k, v in state_dict.items() if k.endswith('num_batches_tracked')}
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                self.lib.nbc_train_destroy(C.c_void_p(self.handle))
+                self.handle = None
+        except Exception:
+            pass
+
+    # -- state_dict <-> flat buffers ---------------------------------------------------------------------------------
+    def _device_tensors(self, sd):
+        out = []
+        for k in self.keys:
+            t = sd[k]
+            if t.dtype == torch.int64:
+                out.append(t.to(self.device))
+            else:
+                out.append(t.detach().to(device=self.device, dtype=torch.float32).contiguous())
+        return out
+
+    def _exchange(self, tensors, flat, stats, direction):
+        arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        _lib.check(self.lib.nbc_train_exchange(C.c_void_p(self.handle), arr, len(tensors), C.c_void_p(flat.data_ptr()),
+                                               C.c_void_p(stats.data_ptr()) if stats is not None else C.c_void_p(0), direction,
+                                               C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
+                   'nbc_train_exchange')
+        torch.cuda.current_stream(self.device).synchronize()
+        return tensors
+
+    def _template(self):
+        import neuralbarkcalculator_b200 as nbc
+        sd = nbc.fcn_resnet50(pretrained=False).state_dict()
+        return {k: torch.zeros_like(v, device=self.device) for k, v in sd.items()}
+
+    def state_dict(self):
+        """Current weights (and BatchNorm running statistics) as a 326-key torchvision-layout state_dict."""
+        with torch.cuda.device(self.device):
+            sd = self._template()
+            self._exchange([sd[k] for k in self.keys], self.params, self.stats, 1)
+        for k in sd:
+            if k.endswith('num_batches_tracked'):
+                sd[k].fill_(self.num_batches_tracked.get(k, 0))
+        return sd
+
+    def gradients(self):
+        """Gradients of the last forward_backward in state_dict layout (OIHW conv weights; BN weight / bias; classifier)."""
+        with torch.cuda.device(self.device):
+            sd = self._template()
+            self._exchange([sd[k] for k in self.keys], self.grads, None, 1)
+        return {k: v for k, v in sd.items() if 'running' not in k and 'num_batches' not in k}
+
+    # -- the step ------------------------------------------------------------------------------------------------------
+    def forward_backward(self, images, targets, seed=0, dropout=None, update_stats=True):
+        """images: u8 NHWC [N,H,W,3] (normalised inside) or f32 NCHW [N,3,H,W]; targets: u8 [N,H,W].
+        Returns the loss (0-dim CUDA tensor); gradients are left in ``self.grads``."""
+        p = self.dropout if dropout is None else dropout
+        if images.dtype == torch.uint8:
+            kind, shape = 0, (self.N, self.H, self.W, 3)
+        elif images.dtype == torch.float32:
+            kind, shape = 1, (self.N, 3, self.H, self.W)
+        else:
+            raise RuntimeError('images must be u8 NHWC or f32 NCHW')
+        if not images.is_cuda or tuple(images.shape) != shape:
+            raise RuntimeError('images must be a CUDA tensor of shape %s' % (shape,))
+        if not targets.is_cuda or targets.dtype != torch.uint8 or tuple(targets.shape) != (self.N, self.H, self.W):
+            raise RuntimeError('targets must be a CUDA u8 tensor [N,H,W]')
+        images, targets = images.contiguous(), targets.contiguous()
+        with torch.cuda.device(self.device):
+            off = (-self.ws.data_ptr()) % 1024
+            _lib.check(self.lib.nbc_train_forward_backward(
+                C.c_void_p(self.handle), C.c_void_p(self.params.data_ptr()),
+                C.c_void_p(self.stats.data_ptr()) if update_stats else C.c_void_p(0), C.c_void_p(self.grads.data_ptr()),
+                C.c_void_p(images.data_ptr()), kind, self.mean3, self.std3, C.c_void_p(targets.data_ptr()),
+                C.c_void_p(self.class_weights.data_ptr()), C.c_float(p), C.c_uint64(seed), C.c_void_p(self.loss.data_ptr()),
+                C.c_void_p(self.ws.data_ptr() + off), C.c_size_t(self.ws.numel() - off),
+                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), 'nbc_train_forward_backward')
+        if update_stats:
+            for k in self.num_batches_tracked:
+                self.num_batches_tracked[k] += 1
+        return self.loss
+
+    def optimizer_step(self):
+        """All-reduce the gradients over the data-parallel group (if any), then one fused Adam pass."""
+        import torch.distributed as dist
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if world > 1:
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
+        self.step_count += 1
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.nbc_train_adam(C.c_void_p(self.params.data_ptr()), C.c_void_p(self.grads.data_ptr()),
+                                               C.c_void_p(self.adam_m.data_ptr()), C.c_void_p(self.adam_v.data_ptr()),
+                                               self.params.numel(), C.c_float(self.lr), C.c_float(self.betas[0]),
+                                               C.c_float(self.betas[1]), C.c_float(self.eps), C.c_float(self.wd), self.step_count,
+                                               C.c_float(1.0 / world),
+                                               C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), 'nbc_train_adam')
+
+    def step(self, images, targets, seed=None):
+        loss = self.forward_backward(images, targets, seed=self.step_count if seed is None else seed)
+        self.optimizer_step()
+        return loss
