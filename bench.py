@@ -36,7 +36,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='predict64', choices=['predict64', 'batch32'])
+    ap.add_argument('--workload', default='predict64', choices=['predict64', 'batch32', 'train'])
     ap.add_argument('--batch', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
@@ -201,6 +201,38 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms, launches
+
+    if args.workload == 'train':
+        # BASELINE.json configs[3]: one training step (fwd + weighted CE + bwd + all-reduce + Adam), batch 8 per GPU
+        from oracle import synth
+        from neuralbarkcalculator_b200.train import Trainer
+        B = args.batch or 8
+        imgs = torch.from_numpy(np.stack([synth.texture_u8(1024, 1024, 100 * rank + i) for i in range(2)])).to(dev)
+        imgs = imgs.repeat((B + 1) // 2, 1, 1, 1)[:B].contiguous()
+        tgt = torch.from_numpy(np.stack([synth.class_mask(1024, 1024, 200 * rank + i) for i in range(2)])).to(dev)
+        tgt = tgt.repeat((B + 1) // 2, 1, 1)[:B].contiguous()
+        tr = Trainer(sd, B, 1024, 1024, device=str(dev), dropout=0.8)
+        res = {}
+
+        def step():
+            res['loss'] = tr.step(imgs, tgt)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        ms, launches = timed(step, args.steps, args.warmup)
+        clocks = sampler.summary()
+        if rank == 0:
+            line = {'metric': 'images/sec (training step)', 'value': world * B * args.steps / (ms / 1000.0), 'unit': 'images/s',
+                    'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+                    'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+                    'config': {'workload': 'training step: FCN-ResNet50 3-class, max-of-index weighted CE, batch %d per GPU at '
+                                           '1024x1024, Adam lr 5e-4 wd 2e-3, dropout 0.8, NCCL all-reduce of the flat gradient '
+                                           'buffer (configs[3])' % B, 'parallelism': 'dp%d' % world},
+                    'clocks': clocks, 'gpu_launches': launches, 'loss': float(res['loss']),
+                    'tflops': 3 * 1106.64e9 * B * args.steps / (ms / 1000.0) / 1e12, 'e2e': None, 'roofline': None, 'cpu_baseline': None}
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     if args.workload == 'batch32':
         B = args.batch or 32

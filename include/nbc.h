@@ -184,6 +184,10 @@ int nbc_train_forward_backward(nbc_train_plan* plan, float* params, float* stats
                                int input_kind, const float* mean3_host, const float* std3_host, const uint8_t* target,
                                const float* weights3, float dropout_p, uint64_t seed, float* loss, void* workspace,
                                size_t workspace_bytes, void* stream);
+/* test / debug accessors: workspace byte offset + {N,H,W,C} of an intermediate (what: 0 z of unit, 1 y of unit,
+ * 2 low-res logits, 3 full-res logits, 4 dL/dfull, 5 dL/dlow); units are in state_dict order (0 = stem). */
+int64_t nbc_train_debug_offset(const nbc_train_plan* plan, int what, int index, int32_t* dims_out);
+int nbc_train_num_units(const nbc_train_plan* plan);
 int nbc_train_adam(float* params, const float* grads, float* adam_m, float* adam_v, int64_t n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 

@@ -60,6 +60,8 @@ SIGNATURES = {
     'nbc_train_forward_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, C.POINTER(c_float),
                                    C.POINTER(c_float), c_void_p, c_void_p, c_float, C.c_uint64, c_void_p, c_void_p, c_size_t,
                                    c_void_p]),
+    'nbc_train_debug_offset': (c_i64, [c_void_p, c_int, c_int, C.POINTER(C.c_int32)]),
+    'nbc_train_num_units': (c_int, [c_void_p]),
     'nbc_train_adam': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float, c_float,
                        c_int, c_float, c_void_p]),
 }

@@ -406,6 +406,29 @@ extern "C" int nbc_train_forward_backward(nbc_train_plan* p, float* params, floa
   return 0;
 }
 
+// debug / test accessor: byte offset into the workspace and geometry of an intermediate tensor.
+// what: 0 = z (pre-BN, bf16 NHWC) of unit `index`, 1 = y (post BN/ReLU) of unit `index`, 2 = low-res logits (f32 planar),
+// 3 = full-res logits (f32 planar), 4 = d loss / d full logits, 5 = d loss / d low-res logits.  dims_out[4] = N,H,W,C.
+extern "C" int64_t nbc_train_debug_offset(const nbc_train_plan* p, int what, int index, int32_t* dims_out) {
+  if (!p || !dims_out) return -1;
+  if (what == 0 || what == 1) {
+    if (index < 0 || index >= (int)p->units.size()) return -1;
+    const Unit& u = p->units[index];
+    dims_out[0] = p->N, dims_out[1] = u.Ho, dims_out[2] = u.Wo, dims_out[3] = u.Cout;
+    return (int64_t)(what == 0 ? u.z_off : u.y_off);
+  }
+  if (what == 2 || what == 5) {
+    dims_out[0] = p->N, dims_out[1] = p->H8, dims_out[2] = p->W8, dims_out[3] = 3;
+    return (int64_t)(what == 2 ? p->low_off : p->dlow_off);
+  }
+  if (what == 3 || what == 4) {
+    dims_out[0] = p->N, dims_out[1] = p->H, dims_out[2] = p->W, dims_out[3] = 3;
+    return (int64_t)(what == 3 ? p->full_off : p->dfull_off);
+  }
+  return -1;
+}
+extern "C" int nbc_train_num_units(const nbc_train_plan* p) { return p ? (int)p->units.size() : 0; }
+
 extern "C" int nbc_train_adam(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1,
                               float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
   NBC_REQUIRE(params && grads && m && v && n > 0 && step >= 1, "nbc_train_adam: bad arguments");

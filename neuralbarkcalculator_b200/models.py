@@ -82,8 +82,9 @@ class SimpleSegmentationModel(nn.Module):
     def _check_eval(self):
         if self.training:
             raise NotImplementedError(
-                'train-mode forward (batch-statistics BN, dropout, backward) is not built yet; call .eval(). '
-                'There is deliberately no PyTorch fallback.')
+                'the module forward is the inference path; call .eval().  Training (train-mode BatchNorm, dropout, backward, '
+                'Adam, NCCL all-reduce) runs natively through neuralbarkcalculator_b200.train.Trainer -- there is '
+                'deliberately no torch-autograd fallback.')
 
     def forward(self, x):
         self._check_eval()

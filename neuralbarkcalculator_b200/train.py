@@ -96,6 +96,19 @@ class Trainer:
             self._exchange([sd[k] for k in self.keys], self.grads, None, 1)
         return {k: v for k, v in sd.items() if 'running' not in k and 'num_batches' not in k}
 
+    def debug_tensor(self, what, index=0):
+        """View of an intermediate of the last step (tests): what 0/1 = z / y of unit ``index`` (bf16 NHWC), 2/3 = low / full
+        resolution logits, 4/5 = their gradients (f32 [N,3,h,w])."""
+        dims = (C.c_int32 * 4)()
+        off = self.lib.nbc_train_debug_offset(C.c_void_p(self.handle), what, index, dims)
+        if off < 0:
+            raise RuntimeError('bad debug tensor request')
+        base = (-self.ws.data_ptr()) % 1024 + off
+        n, h, w, c = [int(v) for v in dims]
+        if what in (0, 1):
+            return self.ws[base:base + n * h * w * c * 2].view(torch.bfloat16).view(n, h, w, c)
+        return self.ws[base:base + n * h * w * c * 4].view(torch.float32).view(n, c, h, w)
+
     # -- the step ------------------------------------------------------------------------------------------------------
     def forward_backward(self, images, targets, seed=0, dropout=None, update_stats=True):
         """images: u8 NHWC [N,H,W,3] (normalised inside) or f32 NCHW [N,3,H,W]; targets: u8 [N,H,W].
