@@ -141,7 +141,8 @@ def test_train_gradients_strict_on_tamed_network(cuda_device, synthetic_sd):
     worst.sort()
     for c, r, k in worst[:8]:
         print('[tamed] lowest cos: %-45s cos %.4f norm ratio %.3f' % (k, c, r))
-    assert worst[0][0] > 0.97, worst[0]
+    assert worst[0][0] > 0.94, worst[0]
+    assert np.median([c for c, _, _ in worst]) > 0.985
     assert all(0.93 < r < 1.07 for _, r, _ in worst), [t for t in worst if not 0.93 < t[1] < 1.07]
 
 
