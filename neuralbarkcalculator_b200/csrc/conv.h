@@ -19,7 +19,7 @@ struct ConvGeom {
 
 // tcgen05 path: tensor maps are encoded once per (shape, pointers) and reused across launches
 struct ConvTcPrepared {
-  alignas(64) unsigned char storage[1024];
+  alignas(64) unsigned char storage[1536];
 };
 bool conv_tc_supported(const ConvGeom& g);
 // valid_h (device, int[N], optional): ragged batch -- valid OUTPUT rows per image (see conv_tc.cu)

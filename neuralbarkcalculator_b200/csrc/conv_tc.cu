@@ -13,9 +13,11 @@
 //   * both land in 128B-swizzled K-major smem and are consumed by tcgen05.mma (M=128, N=BLOCK_N, K=16) issued
 //     by one thread; the f32 accumulator lives in TMEM, double buffered so the epilogue of tile i overlaps the
 //     main loop of tile i+1.
-//   * epilogue (8 warps): tcgen05.ld -> smem transpose -> + bias (+ residual, prefetched) -> ReLU -> bf16 ->
-//     coalesced 16 B stores.
-// Persistent CTAs (one per SM), warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..9 = epilogue.
+//   * epilogue (8 warps): tcgen05.ld -> + bias (+ residual) -> ReLU -> bf16 -> 128B-swizzled staging buffer in
+//     shared memory -> TMA store.  The residual group is prefetched INTO the staging buffer by TMA and updated in
+//     place, so residual reads and output writes are full 128-byte lines issued by the copy engine, not by the LSU.
+// Persistent CTAs (one per SM), warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..9 = epilogue,
+// 10 = output / residual TMA.
 #include "common.cuh"
 #include "conv.h"
 
@@ -24,6 +26,8 @@ namespace nbc {
 struct ConvTcParams {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
+  CUtensorMap tmOut;  // output [N][Ho][Wo][Cout], box {64 ch, tw, th, 1}: one 64-channel group of a tile per TMA store
+  CUtensorMap tmRes;  // residual, same geometry (RES kernels only)
   const float* bias;
   const __nv_bfloat16* residual;
   __nv_bfloat16* out;
@@ -34,7 +38,8 @@ struct ConvTcParams {
   int relu;
   int f16;  // operand / output format: 0 bf16, 1 fp16
   // ragged batches: valid_h[img] = number of valid OUTPUT rows of image img (nullptr: all rows valid).  Rows at or
-  // beyond it are written as zeros for kRaggedHalo rows (the zero padding the next layer reads) and skipped after.
+  // beyond it are written as zeros (at least kRaggedHalo of them: the zero padding the next layer reads); tiles
+  // that start beyond the halo are skipped.
   const int* valid_h;
   int8_t tap_map[9];
   int16_t tap_dh[9];
@@ -42,38 +47,78 @@ struct ConvTcParams {
 };
 
 constexpr int kRaggedHalo = 4;   // >= the largest padding / dilation of any consumer (layer4: dilation 4)
-constexpr int kTcThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kTcThreads = 352;  // warp 0 TMA operands, warp 1 MMA, warps 2..9 epilogue, warp 10 output / residual TMA
+constexpr int kOutBufBytes = 128 * 64 * 2;  // 128 pixels x 64 channels x 16 bit: one output group of a tile
+constexpr int kSmemLimit = 232448;          // 227 KB of dynamic shared memory per CTA on sm_100
 
 // BN = output channels per tile, KBLK = K elements per pipeline stage: 64 (128-byte swizzle) for the bottleneck /
 // head convs, 32 (64-byte swizzle) for the stem, whose K block is one 7-tap row of 8 pixels x 4 channels.
-template <int BN, int KBLK>
+// OB = output staging buffers (16 KB each): 4 when the epilogue sets the pace (residual layers, K <= 512), 2 (and a
+// deeper operand ring) when the MMA main loop does.
+template <int BN, int KBLK, int OB>
 struct TcCfg {
   static constexpr int kABytes = 128 * KBLK * 2;  // 128 pixels x KBLK bf16
   static constexpr int kBBytes = BN * KBLK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStagesMax = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kFixedBytes = OB * kOutBufBytes + 256 /*barriers*/ + 1024 /*align slack*/;
+  static constexpr int kStagesFit = (kSmemLimit - kFixedBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit < kStagesMax ? kStagesFit : kStagesMax;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-  // epilogue transpose tiles (8 warps x 32 rows x 20 words) + per-warp bias slices (8 x BN/2 floats)
-  static constexpr int kStagingBytes = 8 * 32 * 20 * 4 + 8 * (BN / 2) * 4;
-  static constexpr int kUsedBytes = kStages * kStageBytes + 1024 /*barriers*/ + kStagingBytes + 1024 /*align slack*/;
+  static constexpr int kUsedBytes = kStages * kStageBytes + kFixedBytes;
   // > half an SM's shared memory keeps one CTA (one TMEM owner) per SM
   static constexpr int kSmemBytes = kUsedBytes < 120 * 1024 ? 120 * 1024 : kUsedBytes;
   static constexpr uint32_t kSwizzleBytes = KBLK * 2;  // 128 or 64
+  static constexpr int kSteps = BN / 64;                    // 64-channel output groups ("steps") per tile
+  static constexpr int kWarpsPerStep = (BN == 64) ? 8 : 4;  // epilogue warps that fill one staging buffer
+  static_assert(kStages >= 2 && kUsedBytes <= kSmemLimit, "shared memory budget");
 };
 
+struct TileCoord {
+  int img, h0, w0, n_tile;
+};
+__device__ __forceinline__ TileCoord tile_coord(const ConvTcParams& p, int tile) {
+  TileCoord t;
+  t.n_tile = tile % p.num_n_tiles;
+  int m_tile = tile / p.num_n_tiles;
+  const int tw_i = m_tile % p.tiles_w;
+  m_tile /= p.tiles_w;
+  const int th_i = m_tile % p.tiles_h;
+  t.img = m_tile / p.tiles_h;
+  t.w0 = tw_i << p.tw_log2;
+  t.h0 = th_i * p.th;
+  return t;
+}
+// dead tile of a ragged batch: starts at or below the last valid row of its image -> no loads, no MMA
+__device__ __forceinline__ bool tile_dead(const ConvTcParams& p, int tile) {
+  if (p.valid_h == nullptr) return false;
+  const int mt = tile / p.num_n_tiles / p.tiles_w;
+  return (mt % p.tiles_h) * p.th >= __ldg(p.valid_h + mt / p.tiles_h);
+}
+// output group handled by local step j of a tile (see the epilogue): half 0 of the epilogue warps owns the even
+// steps, half 1 the odd ones; each half walks its own contiguous range of channels
+template <int STEPS>
+__device__ __forceinline__ int step_group(int j) {
+  return STEPS == 1 ? 0 : (j & 1) * (STEPS / 2) + (j >> 1);
+}
+
 // RES / RELU / F16 are compile-time so the epilogue inner loop carries no runtime branches: on the low-K layers the
-// epilogue's instruction count per output element, not the MMA, sets the pace.
-template <int BN, int KBLK, bool RES, bool RELU, bool F16>
+// epilogue, not the MMA, sets the pace.
+template <int BN, int KBLK, int OB, bool RES, bool RELU, bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
-  using Cfg = TcCfg<BN, KBLK>;
+  using Cfg = TcCfg<BN, KBLK, OB>;
   constexpr int kABytes = Cfg::kABytes;
+  constexpr int kSteps = Cfg::kSteps;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* obuf = smem + Cfg::kStages * Cfg::kStageBytes;   // OB staging buffers, 1024-aligned (stage sizes are)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(obuf + OB * kOutBufBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* bufready_bar = tempty_bar + 2;    // staging buffer may be used by the epilogue (residual landed / store drained)
+  uint64_t* outready_bar = bufready_bar + OB; // staging buffer holds a finished output group
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(outready_bar + OB);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -87,12 +132,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 8);
     }
+    for (int i = 0; i < OB; ++i) {
+      mbar_init(&bufready_bar[i], 1);
+      mbar_init(&outready_bar[i], Cfg::kWarpsPerStep);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 10 && lane == 0) {
+    tma_prefetch_desc(&p.tmOut);
+    if (RES) tma_prefetch_desc(&p.tmRes);
   }
   tc_fence_before();
   __syncthreads();
@@ -107,22 +160,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.num_n_tiles;
-        int m_tile = tile / p.num_n_tiles;
-        const int tw_i = m_tile % p.tiles_w;
-        m_tile /= p.tiles_w;
-        const int th_i = m_tile % p.tiles_h;
-        const int img = m_tile / p.tiles_h;
-        const int w0 = tw_i << p.tw_log2, h0 = th_i * p.th, n0 = n_tile * BN;
-        if (p.valid_h != nullptr && h0 >= __ldg(p.valid_h + img)) continue;  // dead tile of a ragged batch
+        if (tile_dead(p, tile)) continue;
+        const TileCoord t = tile_coord(p, tile);
+        const int n0 = t.n_tile * BN;
         for (int tap = 0; tap < p.n_taps; ++tap) {
           const CUtensorMap* mA = &p.tmA[p.tap_map[tap]];
-          const int cw = w0 + p.tap_dw[tap], ch = h0 + p.tap_dh[tap];
+          const int cw = t.w0 + p.tap_dw[tap], ch = t.h0 + p.tap_dh[tap];
           for (int cb = 0; cb < p.cblocks; ++cb) {
             mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + (int)stage);
             uint8_t* sA = smem + stage * Cfg::kStageBytes;
             mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_4d(sA, mA, &full_bar[stage], cb * KBLK, cw, ch, img);
+            tma_load_4d(sA, mA, &full_bar[stage], cb * KBLK, cw, ch, t.img);
             tma_load_2d(sA + kABytes, &p.tmB, &full_bar[stage], (tap * p.cblocks + cb) * KBLK, n0);
             if (++stage == Cfg::kStages) {
               stage = 0;
@@ -139,10 +187,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       constexpr uint32_t idesc = F16 ? umma_idesc_f16(128, BN) : umma_idesc_bf16(128, BN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        if (p.valid_h != nullptr) {
-          const int mt = tile / p.num_n_tiles / p.tiles_w;
-          if ((mt % p.tiles_h) * p.th >= __ldg(p.valid_h + mt / p.tiles_h)) continue;
-        }
+        if (tile_dead(p, tile)) continue;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 300 + (int)acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -168,103 +213,122 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       }
     }
     __syncwarp();
+  } else if (warp == 10) {
+    // ================================ output / residual TMA ================================
+    // One thread walks the (live tile, output group) steps in order.  RES: the residual group of step s + OB - 1 is
+    // fetched into its staging buffer while the epilogue warps work on step s; the epilogue adds the accumulator IN
+    // PLACE and the same buffer then leaves through a TMA store (full 128-byte lines, no partial-sector writes).
+    if (elect_one()) {
+      constexpr int kAhead = RES ? OB - 1 : 0;
+      int ld_tile = blockIdx.x;
+      while (ld_tile < total_tiles && tile_dead(p, ld_tile)) ld_tile += gridDim.x;
+      int st_tile = ld_tile, ld_j = 0, st_j = 0;
+      uint32_t ld_s = 0, st_s = 0;
+      auto issue_load = [&]() {
+        const TileCoord t = tile_coord(p, ld_tile);
+        const uint32_t b = ld_s % OB;
+        mbar_expect_tx(&bufready_bar[b], kOutBufBytes);
+        tma_load_4d(obuf + b * kOutBufBytes, &p.tmRes, &bufready_bar[b], t.n_tile * BN + step_group<kSteps>(ld_j) * 64, t.w0,
+                    t.h0, t.img);
+        ++ld_s;
+        if (++ld_j == kSteps) {
+          ld_j = 0;
+          ld_tile += gridDim.x;
+          while (ld_tile < total_tiles && tile_dead(p, ld_tile)) ld_tile += gridDim.x;
+        }
+      };
+      if (RES) {
+        for (int i = 0; i < kAhead && ld_tile < total_tiles; ++i) issue_load();
+      }
+      while (st_tile < total_tiles) {
+        if (RES && ld_tile < total_tiles) {
+          tma_store_wait_read<0>();   // the buffer of step ld_s - OB (= st_s - 1) has been read by its store
+          issue_load();
+        }
+        const uint32_t b = st_s % OB;
+        mbar_wait(&outready_bar[b], (st_s / OB) & 1u, 500 + (int)b);
+        const TileCoord t = tile_coord(p, st_tile);
+        tma_store_4d(&p.tmOut, obuf + b * kOutBufBytes, t.n_tile * BN + step_group<kSteps>(st_j) * 64, t.w0, t.h0, t.img);
+        tma_store_commit();
+        if (!RES) {
+          tma_store_wait_read<0>();
+          mbar_arrive(&bufready_bar[b]);
+        }
+        ++st_s;
+        if (++st_j == kSteps) {
+          st_j = 0;
+          st_tile += gridDim.x;
+          while (st_tile < total_tiles && tile_dead(p, st_tile)) st_tile += gridDim.x;
+        }
+      }
+      tma_store_wait_all();
+    }
+    __syncwarp();
   } else {
     // ================================ epilogue (warps 2..9) ================================
-    // TMEM gives each thread one pixel row of the accumulator; storing that directly would touch 32 different
-    // pixels per instruction.  Each warp therefore transposes 16-column chunks through a private padded smem tile
-    // (pitch 20 words: conflict-free for 16-byte accesses both ways) and does bias / residual / ReLU / bf16 pack in
-    // the "coalesced domain": 2 lanes cover the 32 contiguous bytes a pixel owns in the chunk, 16 pixels per
-    // instruction, for the residual loads and the output stores alike.  Eight warps (two per TMEM lane quarter, each
-    // owning half of the tile's columns) and residual loads issued one chunk ahead keep enough bytes in flight to
-    // hide the L2 / HBM latency on the low-K layers, where this epilogue -- not the MMA -- sets the pace.
+    // TMEM gives each thread one pixel row of the accumulator.  The thread adds bias (+ the residual it finds in the
+    // staging buffer), applies ReLU, packs to 16 bit and writes its row into the 128B-swizzled staging buffer -- the
+    // layout TMA expects -- at the very address the residual came from.  16-byte unit u of row r lives at
+    // r * 128 + ((u ^ (r & 7)) << 4): the 8 lanes of a quarter-warp hit 8 different units, i.e. all 32 banks.
     const int ew = warp - 2;
     const int q = warp & 3;          // TMEM lane quarter this warp may access
-    const int half = ew >> 2;        // which half of the BN columns
-    constexpr int kCols = BN / 2;    // columns per warp
-    float* stg = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 1024) + ew * (32 * 20);
-    float* sbias = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 1024 + 8 * 32 * 20 * 4) + ew * kCols;
-    // lane -> (row, 8-column piece) of the coalesced domain.  A quarter-warp (the unit the smem banks are resolved for
-    // 16-byte accesses) reads 8 different rows of the same piece: with the 20-word pitch that is conflict-free, and the
-    // global side still sees 16 rows x 32 contiguous bytes per instruction.
-    const int crow = (lane & 7) + ((lane >> 4) << 3), cpiece = (lane >> 3) & 1;
-    uint32_t acc = 0, acc_phase = 0;
+    const int half = ew >> 2;        // BN >= 128: which steps of the tile; BN == 64: which 32 of the 64 columns
+    constexpr int kUnits = (BN == 64) ? 4 : 8;            // 16-byte units (8 channels) per row this warp handles per step
+    constexpr int kMySteps = (BN == 64) ? 1 : kSteps / 2;  // steps per tile of this warp
+    const int row = q * 32 + lane;                         // pixel of the tile == TMEM lane == staging row
+    const uint32_t row_off = (uint32_t)row * 128u;
+    const uint32_t rsw = (uint32_t)(row & 7);
+    const int u0 = (BN == 64) ? half * 4 : 0;
+    uint32_t acc = 0, acc_phase = 0, live_tiles = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.num_n_tiles;
-      int m_tile = tile / p.num_n_tiles;
-      const int tw_i = m_tile % p.tiles_w;
-      m_tile /= p.tiles_w;
-      const int th_i = m_tile % p.tiles_h;
-      const int img = m_tile / p.tiles_h;
-      const int n0 = n_tile * BN + half * kCols;
-      __nv_bfloat16* optr[2];          // this lane's two output rows of the tile, at its 8-column piece
-      const __nv_bfloat16* rptr[2];
-      bool ok[2];     // this row is stored
-      bool live[2];   // ... with computed values (otherwise zeros: the halo rows of a ragged batch)
-      const int vh = p.valid_h != nullptr ? __ldg(p.valid_h + img) : INT_MAX;
-      const int vz = p.valid_h != nullptr ? vh + kRaggedHalo : INT_MAX;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int row = q * 32 + crow + 16 * j;
-        const int w = (tw_i << p.tw_log2) + (row & (p.tw - 1)), h = th_i * p.th + (row >> p.tw_log2);
-        ok[j] = (w < p.Wo) && (h < p.Ho) && (h < vz);
-        live[j] = h < vh;
-        const int64_t off = (((int64_t)img * p.Ho + h) * p.Wo + w) * p.Cout + n0 + cpiece * 8;
-        optr[j] = p.out + off;
-        rptr[j] = RES ? p.residual + off : nullptr;
-      }
-      if (th_i * p.th >= vh) {
-        // dead tile: no MMA was issued for it; only the zero halo is written
-        if (th_i * p.th < vz) {
-          for (int c = 0; c < kCols; c += 16)
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-              if (ok[j]) *reinterpret_cast<uint4*>(optr[j] + c) = make_uint4(0u, 0u, 0u, 0u);
+      const TileCoord t = tile_coord(p, tile);
+      const int vh = p.valid_h != nullptr ? __ldg(p.valid_h + t.img) : INT_MAX;
+      const int h = t.h0 + (row >> p.tw_log2), w = t.w0 + (row & (p.tw - 1));
+      if (t.h0 >= vh) {
+        // dead tile: no MMA was issued for it; only the zero halo is written (plain stores, rare)
+        if (t.h0 < vh + kRaggedHalo && w < p.Wo && h < p.Ho && h < vh + kRaggedHalo) {
+          constexpr int kColsZ = BN / 2;
+          __nv_bfloat16* o = p.out + (((int64_t)t.img * p.Ho + h) * p.Wo + w) * p.Cout + t.n_tile * BN + half * kColsZ;
+          for (int c = 0; c < kColsZ; c += 8) *reinterpret_cast<uint4*>(o + c) = make_uint4(0u, 0u, 0u, 0u);
         }
         continue;
       }
-      const bool st0 = ok[0], st1 = ok[1];
-      const bool lv0 = ok[0] && live[0], lv1 = ok[1] && live[1];
-      // All global loads of the tile are issued BEFORE waiting for the accumulator, so their latency hides behind
-      // the MMA main loop: the whole residual tile sits in registers (2 x 16 B per 16-column chunk per lane), the
-      // bias slice of this warp goes to its private smem row.
-      constexpr int kChunks = kCols / 16;
-      uint4 res[kChunks][2];
-      if (RES) {
-#pragma unroll
-        for (int ci = 0; ci < kChunks; ++ci) {
-          if (lv0) res[ci][0] = __ldg(reinterpret_cast<const uint4*>(rptr[0] + ci * 16));
-          if (lv1) res[ci][1] = __ldg(reinterpret_cast<const uint4*>(rptr[1] + ci * 16));
-        }
-      }
-      __syncwarp();   // previous tile's readers of sbias are done
-      for (int i = lane; i < kCols; i += 32) sbias[i] = __ldg(p.bias + n0 + i);
-      __syncwarp();
+      const bool live = h < vh;
       mbar_wait(&tfull_bar[acc], acc_phase, 400 + (int)acc);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * kCols;
-      float4* const wr = reinterpret_cast<float4*>(stg + lane * 20);
-      const float4* const rd0 = reinterpret_cast<const float4*>(stg + crow * 20 + cpiece * 8);
-      const float4* const rd1 = reinterpret_cast<const float4*>(stg + (crow + 16) * 20 + cpiece * 8);
 #pragma unroll
-      for (int ci = 0; ci < kChunks; ++ci) {
-        const int c = ci * 16;
-        uint32_t r[16];
-        tmem_ld16(t_row + c, r);
-        const float4 b0 = *reinterpret_cast<const float4*>(sbias + c + cpiece * 8);
-        const float4 b1 = *reinterpret_cast<const float4*>(sbias + c + cpiece * 8 + 4);
+      for (int i = 0; i < kMySteps; ++i) {
+        const int j = (BN == 64) ? 0 : half + 2 * i;
+        const int grp = step_group<kSteps>(j);
+        const uint32_t s = live_tiles * kSteps + j;
+        const uint32_t b = s % OB;
+        const int col0 = grp * 64 + u0 * 8;    // first column (within the BN tile) of this warp's units
+        uint32_t a[kUnits * 8];
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + col0;
+#pragma unroll
+        for (int k = 0; k < kUnits / 4; ++k) tmem_ld32(t_addr + 32 * k, reinterpret_cast<uint32_t(&)[32]>(a[32 * k]));
+        const float* bptr = p.bias + t.n_tile * BN + col0;
+        mbar_wait(&bufready_bar[b], RES ? ((s / OB) & 1u) : (((s / OB) & 1u) ^ 1u), 600 + (int)b);
         tmem_ld_wait();
+        if (i == kMySteps - 1) {
+          // the accumulator is in registers: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        uint8_t* rowp = obuf + b * kOutBufBytes + row_off;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          wr[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
-                              __uint_as_float(r[4 * i + 3]));
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const float4* rd = j == 0 ? rd0 : rd1;
-          const float4 v0 = rd[0], v1 = rd[1];
-          float v[8] = {v0.x + b0.x, v0.y + b0.y, v0.z + b0.z, v0.w + b0.w, v1.x + b1.x, v1.y + b1.y, v1.z + b1.z, v1.w + b1.w};
+        for (int u = 0; u < kUnits; ++u) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bptr + u * 8));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bptr + u * 8 + 4));
+          uint4* sp = reinterpret_cast<uint4*>(rowp + ((((uint32_t)(u0 + u)) ^ rsw) << 4));
+          float v[8] = {__uint_as_float(a[u * 8 + 0]) + b0.x, __uint_as_float(a[u * 8 + 1]) + b0.y,
+                        __uint_as_float(a[u * 8 + 2]) + b0.z, __uint_as_float(a[u * 8 + 3]) + b0.w,
+                        __uint_as_float(a[u * 8 + 4]) + b1.x, __uint_as_float(a[u * 8 + 5]) + b1.y,
+                        __uint_as_float(a[u * 8 + 6]) + b1.z, __uint_as_float(a[u * 8 + 7]) + b1.w};
           if (RES) {
-            const uint32_t rv[4] = {res[ci][j].x, res[ci][j].y, res[ci][j].z, res[ci][j].w};
+            const uint4 r4 = *sp;
+            const uint32_t rv[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) v[2 * k] += lo16(rv[k], F16), v[2 * k + 1] += hi16(rv[k], F16);
           }
@@ -274,15 +338,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           }
           uint4 o = make_uint4(pack16x2(v[0], v[1], F16), pack16x2(v[2], v[3], F16), pack16x2(v[4], v[5], F16),
                                pack16x2(v[6], v[7], F16));
-          const bool lv = j == 0 ? lv0 : lv1;
-          if (!lv) o = make_uint4(0u, 0u, 0u, 0u);     // halo row of a ragged batch (or garbage from a dead residual)
-          if (j == 0 ? st0 : st1) *reinterpret_cast<uint4*>(optr[j] + c) = o;
+          if (!live) o = make_uint4(0u, 0u, 0u, 0u);   // rows below the image in a ragged batch: the next layer's zero padding
+          *sp = o;
         }
+        fence_proxy_async();   // make this thread's staging writes visible to the TMA (async proxy) store
         __syncwarp();
+        if (lane == 0) mbar_arrive(&outready_bar[b]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      ++live_tiles;
       acc ^= 1u;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -357,7 +420,22 @@ struct ConvTcLaunch {
   int block_n;
   int kblk;
   int grid;
+  int out_bufs;
 };
+
+// output (and residual) as [N][Ho][Wo][Cout] with the box of one 64-channel group of a tile
+static int encode_out_maps(ConvTcParams* p, int N, int Ho, int Wo, int Cout, const void* y, const void* residual) {
+  const uint64_t eb = 2;
+  int rc = encode_act_map(&p->tmOut, y, (uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N, (uint64_t)Cout * eb,
+                          (uint64_t)Wo * Cout * eb, (uint64_t)Ho * Wo * Cout * eb, p->tw, p->th);
+  if (rc) return rc;
+  if (residual != nullptr)
+    rc = encode_act_map(&p->tmRes, residual, (uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N, (uint64_t)Cout * eb,
+                        (uint64_t)Wo * Cout * eb, (uint64_t)Ho * Wo * Cout * eb, p->tw, p->th);
+  else
+    p->tmRes = p->tmOut;
+  return rc;
+}
 
 // 128-pixel output rectangle: fewest tiles, widest on ties
 static void choose_tile(int Ho, int Wo, ConvTcParams* p) {
@@ -434,37 +512,45 @@ static int build_launch(const ConvGeom& g, const void* x, const void* w, const f
   }
   int rc = encode_weight_map(&p.tmB, w, (uint64_t)p.n_taps * g.Cin, g.Cout, bn);
   if (rc) return rc;
+  rc = encode_out_maps(&p, g.N, Ho, Wo, g.Cout, y, residual);
+  if (rc) return rc;
+  L->out_bufs = (residual != nullptr || p.n_taps * p.cblocks <= 8) ? 4 : 2;
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int sms = sm_count();
   L->grid = total < sms ? total : sms;
   return 0;
 }
 
-template <int BN, int KBLK, bool RES, bool RELU, bool F16>
+template <int BN, int KBLK, int OB, bool RES, bool RELU, bool F16>
 static int launch_one(const ConvTcLaunch& L, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    NBC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KBLK, RES, RELU, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  TcCfg<BN, KBLK>::kSmemBytes));
+    NBC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, KBLK, OB, RES, RELU, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TcCfg<BN, KBLK, OB>::kSmemBytes));
     attr_set = true;
   }
-  conv_tc_kernel<BN, KBLK, RES, RELU, F16><<<L.grid, kTcThreads, TcCfg<BN, KBLK>::kSmemBytes, stream>>>(L.p);
+  conv_tc_kernel<BN, KBLK, OB, RES, RELU, F16><<<L.grid, kTcThreads, TcCfg<BN, KBLK, OB>::kSmemBytes, stream>>>(L.p);
   NBC_CHECK_LAUNCH();
   return 0;
 }
 
 template <int BN, int KBLK>
 static int launch_bn(const ConvTcLaunch& L, cudaStream_t stream) {
-  const int key = (L.p.residual != nullptr ? 4 : 0) | (L.p.relu ? 2 : 0) | (L.p.f16 ? 1 : 0);
+  const bool res = L.p.residual != nullptr;
+  const int key = (res ? 8 : (L.out_bufs == 4 ? 4 : 0)) | (L.p.relu ? 2 : 0) | (L.p.f16 ? 1 : 0);
   switch (key) {
-    case 0: return launch_one<BN, KBLK, false, false, false>(L, stream);
-    case 1: return launch_one<BN, KBLK, false, false, true>(L, stream);
-    case 2: return launch_one<BN, KBLK, false, true, false>(L, stream);
-    case 3: return launch_one<BN, KBLK, false, true, true>(L, stream);
-    case 4: return launch_one<BN, KBLK, true, false, false>(L, stream);
-    case 5: return launch_one<BN, KBLK, true, false, true>(L, stream);
-    case 6: return launch_one<BN, KBLK, true, true, false>(L, stream);
-    default: return launch_one<BN, KBLK, true, true, true>(L, stream);
+    case 0: return launch_one<BN, KBLK, 2, false, false, false>(L, stream);
+    case 1: return launch_one<BN, KBLK, 2, false, false, true>(L, stream);
+    case 2: return launch_one<BN, KBLK, 2, false, true, false>(L, stream);
+    case 3: return launch_one<BN, KBLK, 2, false, true, true>(L, stream);
+    case 4: return launch_one<BN, KBLK, 4, false, false, false>(L, stream);
+    case 5: return launch_one<BN, KBLK, 4, false, false, true>(L, stream);
+    case 6: return launch_one<BN, KBLK, 4, false, true, false>(L, stream);
+    case 7: return launch_one<BN, KBLK, 4, false, true, true>(L, stream);
+    case 8: return launch_one<BN, KBLK, 4, true, false, false>(L, stream);
+    case 9: return launch_one<BN, KBLK, 4, true, false, true>(L, stream);
+    case 10: return launch_one<BN, KBLK, 4, true, true, false>(L, stream);
+    default: return launch_one<BN, KBLK, 4, true, true, true>(L, stream);
   }
 }
 
@@ -496,6 +582,9 @@ int conv_tc_prepare_stem(int N, int Ho, int Wo, int Hp, int Wp, const void* padd
   for (int ky = 0; ky < 7; ++ky) p.tap_map[ky] = (int8_t)(ky & 1), p.tap_dh[ky] = (int16_t)(ky >> 1), p.tap_dw[ky] = 0;
   int rc = encode_weight_map(&p.tmB, w224, 224, 64, 64, 32);
   if (rc) return rc;
+  rc = encode_out_maps(&p, N, Ho, Wo, 64, y, nullptr);
+  if (rc) return rc;
+  L->out_bufs = 4;
   const int total = p.num_m_tiles;
   const int sms = sm_count();
   L->grid = total < sms ? total : sms;
@@ -507,6 +596,10 @@ int conv_tc_prepare(const ConvGeom& g, const void* x, const void* w, const float
   static_assert(sizeof(ConvTcLaunch) <= sizeof(out->storage), "ConvTcPrepared::storage too small");
   if (!conv_tc_supported(g)) {
     set_error("conv_tc: unsupported shape Cin=%d Cout=%d k=%dx%d stride=%d", g.Cin, g.Cout, g.kh, g.kw, g.stride);
+    return NBC_ERR_INVALID;
+  }
+  if ((reinterpret_cast<uintptr_t>(bias) & 15) != 0) {
+    set_error("conv_tc: bias must be 16-byte aligned");
     return NBC_ERR_INVALID;
   }
   ConvTcLaunch* L = reinterpret_cast<ConvTcLaunch*>(out->storage);
