@@ -78,6 +78,11 @@ typedef struct {
 int nbc_conv_bf16(const nbc_conv_desc* desc, const void* x, const void* w_packed, const float* bias,
                   const void* residual, void* y, void* stream);
 
+/* Weight gradient of the same layer (training path, __main__.py:231-269 backward of every nn.Conv2d):
+ * dw[Cout][kh][kw][Cin] (f32) += sum over output pixels of dz[N,Ho,Wo,Cout]^T * x[N,H,W,Cin] (both bf16 NHWC);
+ * accumulates into dw (zero it first).  desc.impl: 0 = auto, 1 = tcgen05 (MN-major operands), 2 = mma.sync. */
+int nbc_conv_wgrad_bf16(const nbc_conv_desc* desc, const void* dz, const void* x, float* dw, void* stream);
+
 /* ---- stem: ToTensor + Normalize + conv1 7x7/2 + bn1 + relu, then maxpool 3x3/2
  *      (dataset.py:181-190, models.py:233-237, torchvision resnet50 stem) ---------------------------------------
  * img: u8 NHWC [N,H,W,3]; w_stem: f32 [64][7][7][3] BN-folded; out: bf16 NHWC [N,ceil(H/2),ceil(W/2),64]. */
@@ -188,6 +193,8 @@ int nbc_train_forward_backward(nbc_train_plan* plan, float* params, float* stats
  * 2 low-res logits, 3 full-res logits, 4 dL/dfull, 5 dL/dlow); units are in state_dict order (0 = stem). */
 int64_t nbc_train_debug_offset(const nbc_train_plan* plan, int what, int index, int32_t* dims_out);
 int nbc_train_num_units(const nbc_train_plan* plan);
+/* weight-gradient kernels used by the plan: 0 = tcgen05 (default), 1 = mma.sync / CUDA-core cross-check kernels */
+int nbc_train_set_wgrad_impl(nbc_train_plan* plan, int impl);
 int nbc_train_adam(float* params, const float* grads, float* adam_m, float* adam_v, int64_t n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 

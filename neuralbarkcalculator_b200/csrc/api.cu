@@ -3,6 +3,7 @@
 
 #include "common.cuh"
 #include "conv.h"
+#include "train.h"
 
 namespace nbc {
 
@@ -132,5 +133,18 @@ extern "C" int nbc_conv_bf16(const nbc_conv_desc* d, const void* x, const void* 
   if (d->impl == 1 || (d->impl == 0 && tc_ok)) return conv_tc(g, x, w_packed, bias, residual, y, stream);
   if (d->impl == 2 || d->impl == 0) return conv_mma(g, x, w_packed, bias, residual, y, stream);
   set_error("nbc_conv_bf16: unknown impl %d", d->impl);
+  return NBC_ERR_INVALID;
+}
+
+extern "C" int nbc_conv_wgrad_bf16(const nbc_conv_desc* d, const void* dz, const void* x, float* dw, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  NBC_REQUIRE(d && dz && x && dw, "nbc_conv_wgrad_bf16: null pointer");
+  NBC_REQUIRE(!d->f16, "nbc_conv_wgrad_bf16: the training path is bf16 only");
+  ConvGeom g{d->N, d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, d->stride, d->pad, d->dil, 0, 0};
+  NBC_REQUIRE(g.N > 0 && g.H > 0 && g.W > 0 && g.Ho() > 0 && g.Wo() > 0, "nbc_conv_wgrad_bf16: bad shape");
+  const bool tc_ok = wgrad_tc_supported(g);
+  if (d->impl == 1 || (d->impl == 0 && tc_ok)) return wgrad_tc(g, dz, x, dw, stream);
+  if (d->impl == 2 || d->impl == 0) return wgrad_mma(g, dz, x, dw, stream);
+  set_error("nbc_conv_wgrad_bf16: unknown impl %d", d->impl);
   return NBC_ERR_INVALID;
 }

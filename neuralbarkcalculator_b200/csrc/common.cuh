@@ -58,6 +58,10 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 encode_tiled_fn get_encode_tiled();
+// 4-D activation tensor map {C, W, H, N} with a {boxC, boxW, boxH, 1} box (conv_tc.cu); boxC = 64 -> 128B swizzle,
+// boxC = 32 -> 64B swizzle.  Strides in bytes.
+int conv_encode_act_map(CUtensorMap* m, const void* base, uint64_t C, uint64_t Wd, uint64_t Hd, uint64_t Nd, uint64_t strideW,
+                        uint64_t strideH, uint64_t strideN, uint32_t boxW, uint32_t boxH, uint32_t boxC = 64);
 
 // ---- device side ------------------------------------------------------------------------------------------
 #ifdef __CUDACC__

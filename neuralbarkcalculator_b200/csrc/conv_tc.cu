@@ -404,6 +404,11 @@ static int encode_weight_map(CUtensorMap* m, const void* base, uint64_t K, uint6
   return 0;
 }
 
+int conv_encode_act_map(CUtensorMap* m, const void* base, uint64_t C, uint64_t Wd, uint64_t Hd, uint64_t Nd, uint64_t strideW,
+                        uint64_t strideH, uint64_t strideN, uint32_t boxW, uint32_t boxH, uint32_t boxC) {
+  return encode_act_map(m, base, C, Wd, Hd, Nd, strideW, strideH, strideN, boxW, boxH, boxC);
+}
+
 bool conv_tc_supported(const ConvGeom& g) {
   if (g.Cin % 64 != 0 || g.Cout % 64 != 0) return false;
   if (g.kh * g.kw > 9) return false;

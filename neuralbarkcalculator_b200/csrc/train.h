@@ -21,8 +21,14 @@ int dgrad_pack(const float* w_ohwi, int Cout, int Cin, int kh, int kw, void* out
 int oihw_ohwi(const float* src, int Cout, int Cin, int kh, int kw, float* dst, int reverse, cudaStream_t stream);
 // dW[Cout][kh][kw][Cin] (f32, accumulated with atomics) += dz^T * x over all output pixels
 int wgrad_mma(const ConvGeom& g, const void* dz, const void* x, float* dw, cudaStream_t stream);
+// the same on the tcgen05 tensor cores (wgrad_tc.cu); Cin % 64 == 0, Cout % 64 == 0, stride 1 or 2
+bool wgrad_tc_supported(const ConvGeom& g);
+int wgrad_tc(const ConvGeom& g, const void* dz, const void* x, float* dw, cudaStream_t stream);
+int stem_wgrad_tc(const void* dz, const void* padded, int N, int Ho, int Wo, float* dw, cudaStream_t stream);
 
-int maxpool_backward(const void* x, const void* dy, int N, int H, int W, int C, void* dx, cudaStream_t stream);
+// 3x3/2 max pooling that records the position of the first maximum (idx: one byte per output element), and its backward
+int maxpool_forward_idx(const void* x, int N, int H, int W, int C, void* y, void* idx, cudaStream_t stream);
+int maxpool_backward(const void* dy, const void* idx, int N, int H, int W, int C, void* dx, cudaStream_t stream);
 // stem: dW f32 [64][7][7][3] += dz^T * padded image (the bf16 staging buffer [N][2Ho+5][2Wo+6][4] of the stem)
 int stem_wgrad(const void* dz, const void* padded, int N, int Ho, int Wo, float* dw, cudaStream_t stream);
 int dropout_apply(const void* x, int64_t n, float p, uint64_t seed, void* y, cudaStream_t stream);

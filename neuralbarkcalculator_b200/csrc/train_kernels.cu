@@ -17,42 +17,102 @@
 
 namespace nbc {
 
-// ------------------------------------------------------------------------------------------------ BN statistics
-// z: [M][C] 16-bit.  Each block owns a slab of rows; thread t handles channel pairs t, t+blockDim, ...
-// partial: [nblocks][C][2] f32 (sum, sum of squares about the first row's value is not needed: values are O(1)).
-constexpr int kBnRowsPerBlock = 256;
+// ------------------------------------------------------------------------------------------------ BN reductions
+// z: [M][C] 16-bit.  Each block owns a slab of rows.  Thread t covers the 8 channels of 16-byte vector (t % VL) on
+// the rows rl, rl + RL, ... of the slab (VL = min(C/8, 256) vectors per row pass, RL = 256 / VL row lanes), so every
+// warp instruction reads whole 128-byte lines whatever C is; the RL row lanes are then summed through shared memory.
+// partial: [nblocks][C][2] f32.
+constexpr int kBnThreads = 256;
+constexpr int kBnMaxBlocks = 148 * 8;
 
-__global__ void __launch_bounds__(256) bn_stats_partial(const uint32_t* __restrict__ z2, int64_t M, int C,
-                                                        float* __restrict__ partial) {
-  const int C2 = C >> 1;
-  const int64_t r0 = (int64_t)blockIdx.x * kBnRowsPerBlock;
-  const int64_t r1 = min(M, r0 + kBnRowsPerBlock);
-  for (int c2 = threadIdx.x; c2 < C2; c2 += blockDim.x) {
-    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-    for (int64_t r = r0; r < r1; ++r) {
-      const uint32_t v = __ldg(z2 + r * C2 + c2);
-      const float a = bf16lo(v), b = bf16hi(v);
-      s0 += a, q0 = fmaf(a, a, q0), s1 += b, q1 = fmaf(b, b, q1);
+static int bn_blocks(int64_t M) {
+  const int64_t nb = ceil_div64(M, 32);
+  return (int)(nb < kBnMaxBlocks ? (nb < 1 ? 1 : nb) : kBnMaxBlocks);
+}
+
+// sums the RL row-lane copies of the block's 16 * VL accumulators and writes them to partial[blockIdx.x]
+__device__ __forceinline__ void bn_block_reduce(float (&acc)[16], float* red /* [RL][VL*16] smem */, int VL, int RL, int v0,
+                                                int rl, bool active, int v /* vector index this pass */, int C,
+                                                float* __restrict__ partial) {
+  if (RL == 1) {
+    if (active) {
+      float4* o = reinterpret_cast<float4*>(partial + ((int64_t)blockIdx.x * C + (int64_t)v * 8) * 2);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
     }
-    float* o = partial + ((int64_t)blockIdx.x * C + 2 * c2) * 2;
-    o[0] = s0, o[1] = q0, o[2] = s1, o[3] = q1;
+    return;
+  }
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) red[(rl * VL + v0) * 16 + k] = acc[k];
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < VL * 16; o += kBnThreads) {
+    float sum = 0.f;
+    for (int r = 0; r < RL; ++r) sum += red[r * VL * 16 + o];
+    partial[(int64_t)blockIdx.x * C * 2 + o] = sum;   // o = (v * 8 + e) * 2 + which, v < VL = C / 8
   }
 }
 
-// one thread per channel: sums the partials in double, produces the affine a = gamma*invstd, b = beta - mean*a,
+__global__ void __launch_bounds__(kBnThreads) bn_stats_partial(const uint4* __restrict__ z, int64_t M, int C,
+                                                               int64_t rows_per_block, float* __restrict__ partial) {
+  __shared__ float red[kBnThreads * 16];
+  const int vecs = C >> 3;
+  const int VL = vecs < kBnThreads ? vecs : kBnThreads, RL = kBnThreads / VL;
+  const int v0 = threadIdx.x % VL, rl = threadIdx.x / VL;
+  const bool active = rl < RL;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(M, r0 + rows_per_block);
+  for (int v = v0; v < vecs; v += VL) {
+    float acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+    if (active) {
+#pragma unroll 4
+      for (int64_t r = r0 + rl; r < r1; r += RL) {
+        const uint4 q = __ldg(z + r * vecs + v);
+        const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float a = bf16lo(u[k]), b = bf16hi(u[k]);
+          acc[4 * k] += a, acc[4 * k + 1] = fmaf(a, a, acc[4 * k + 1]);
+          acc[4 * k + 2] += b, acc[4 * k + 3] = fmaf(b, b, acc[4 * k + 3]);
+        }
+      }
+    }
+    bn_block_reduce(acc, red, VL, RL, v0, rl, active, v, C, partial);
+  }
+}
+
+// warp-wide sum of the per-block partials of one channel (two values), in double
+__device__ __forceinline__ void bn_sum_partials(const float* __restrict__ partial, int nblocks, int C, int c, double& s,
+                                                double& q) {
+  const int lane = threadIdx.x & 31;
+  s = 0.0, q = 0.0;
+  for (int i = lane; i < nblocks; i += 32) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(partial + ((int64_t)i * C + c) * 2));
+    s += (double)v.x, q += (double)v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+}
+
+// one warp per channel: sums the partials in double, produces the affine a = gamma*invstd, b = beta - mean*a,
 // saves mean / invstd for the backward and updates the running statistics like torch (momentum, unbiased var)
-__global__ void bn_stats_finalize(const float* __restrict__ partial, int nblocks, int C, int64_t M,
+__global__ void __launch_bounds__(256) bn_stats_finalize(const float* __restrict__ partial, int nblocks, int C, int64_t M,
                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                                   float* __restrict__ running_mean, float* __restrict__ running_var,
                                   float* __restrict__ save_mean, float* __restrict__ save_invstd, float* __restrict__ a_out,
                                   float* __restrict__ b_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int i = 0; i < nblocks; ++i) {
-    s += (double)partial[((int64_t)i * C + c) * 2];
-    q += (double)partial[((int64_t)i * C + c) * 2 + 1];
-  }
+  double s, q;
+  bn_sum_partials(partial, nblocks, C, c, s, q);
+  if ((threadIdx.x & 31) != 0) return;
   const double mean = s / (double)M;
   double var = q / (double)M - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -82,11 +142,15 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
       const uint4 rv = __ldg(residual + i);
       rr[0] = rv.x, rr[1] = rv.y, rr[2] = rv.z, rr[3] = rv.w;
     }
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(a + c)), a1 = __ldg(reinterpret_cast<const float4*>(a + c + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + c)), b1 = __ldg(reinterpret_cast<const float4*>(b + c + 4));
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     uint32_t o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float f0 = fmaf(bf16lo(u[k]), __ldg(a + c + 2 * k), __ldg(b + c + 2 * k));
-      float f1 = fmaf(bf16hi(u[k]), __ldg(a + c + 2 * k + 1), __ldg(b + c + 2 * k + 1));
+      float f0 = fmaf(bf16lo(u[k]), av[2 * k], bv[2 * k]);
+      float f1 = fmaf(bf16hi(u[k]), av[2 * k + 1], bv[2 * k + 1]);
       if (residual != nullptr) f0 += bf16lo(rr[k]), f1 += bf16hi(rr[k]);
       if (relu) f0 = fmaxf(f0, 0.f), f1 = fmaxf(f1, 0.f);
       o[k] = pack_bf16x2(f0, f1);
@@ -97,43 +161,55 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
 
 // ------------------------------------------------------------------------------------------------ BN backward
 // partial: [nblocks][C][2] = (sum g, sum g * xhat) with g = dy * (y > 0 if relu), xhat = (z - mean) * invstd
-__global__ void __launch_bounds__(256) bn_bwd_partial(const uint32_t* __restrict__ dy2, const uint32_t* __restrict__ y2,
-                                                      const uint32_t* __restrict__ z2, const float* __restrict__ mean,
-                                                      const float* __restrict__ invstd, int64_t M, int C, int relu,
-                                                      float* __restrict__ partial) {
-  const int C2 = C >> 1;
-  const int64_t r0 = (int64_t)blockIdx.x * kBnRowsPerBlock;
-  const int64_t r1 = min(M, r0 + kBnRowsPerBlock);
-  for (int c2 = threadIdx.x; c2 < C2; c2 += blockDim.x) {
-    const float m0 = mean[2 * c2], m1 = mean[2 * c2 + 1], i0 = invstd[2 * c2], i1 = invstd[2 * c2 + 1];
-    float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
-    for (int64_t r = r0; r < r1; ++r) {
-      const uint32_t g = __ldg(dy2 + r * C2 + c2);
-      float g0 = bf16lo(g), g1 = bf16hi(g);
-      if (relu) {
-        const uint32_t yy = __ldg(y2 + r * C2 + c2);
-        if (!(bf16lo(yy) > 0.f)) g0 = 0.f;
-        if (!(bf16hi(yy) > 0.f)) g1 = 0.f;
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_partial(const uint4* __restrict__ dy, const uint4* __restrict__ y,
+                                                             const uint4* __restrict__ z, const float* __restrict__ mean,
+                                                             const float* __restrict__ invstd, int64_t M, int C, int relu,
+                                                             int64_t rows_per_block, float* __restrict__ partial) {
+  __shared__ float red[kBnThreads * 16];
+  const int vecs = C >> 3;
+  const int VL = vecs < kBnThreads ? vecs : kBnThreads, RL = kBnThreads / VL;
+  const int v0 = threadIdx.x % VL, rl = threadIdx.x / VL;
+  const bool active = rl < RL;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(M, r0 + rows_per_block);
+  for (int v = v0; v < vecs; v += VL) {
+    float acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+    if (active) {
+      const float4 m0 = __ldg(reinterpret_cast<const float4*>(mean + v * 8)), m1 = __ldg(reinterpret_cast<const float4*>(mean + v * 8 + 4));
+      const float4 i0 = __ldg(reinterpret_cast<const float4*>(invstd + v * 8)), i1 = __ldg(reinterpret_cast<const float4*>(invstd + v * 8 + 4));
+      const float mv[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+      const float iv[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll 2
+      for (int64_t r = r0 + rl; r < r1; r += RL) {
+        const uint4 gq = __ldg(dy + r * vecs + v), zq = __ldg(z + r * vecs + v);
+        uint4 yq = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);   // "positive" when there is no ReLU
+        if (relu) yq = __ldg(y + r * vecs + v);
+        const uint32_t gu[4] = {gq.x, gq.y, gq.z, gq.w}, zu[4] = {zq.x, zq.y, zq.z, zq.w}, yu[4] = {yq.x, yq.y, yq.z, yq.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float g0 = bf16lo(gu[k]), g1 = bf16hi(gu[k]);
+          if (!(bf16lo(yu[k]) > 0.f)) g0 = 0.f;
+          if (!(bf16hi(yu[k]) > 0.f)) g1 = 0.f;
+          acc[4 * k] += g0, acc[4 * k + 1] = fmaf(g0, (bf16lo(zu[k]) - mv[2 * k]) * iv[2 * k], acc[4 * k + 1]);
+          acc[4 * k + 2] += g1, acc[4 * k + 3] = fmaf(g1, (bf16hi(zu[k]) - mv[2 * k + 1]) * iv[2 * k + 1], acc[4 * k + 3]);
+        }
       }
-      const uint32_t zz = __ldg(z2 + r * C2 + c2);
-      s0 += g0, s1 += g1;
-      t0 = fmaf(g0, (bf16lo(zz) - m0) * i0, t0), t1 = fmaf(g1, (bf16hi(zz) - m1) * i1, t1);
     }
-    float* o = partial + ((int64_t)blockIdx.x * C + 2 * c2) * 2;
-    o[0] = s0, o[1] = t0, o[2] = s1, o[3] = t1;
+    bn_block_reduce(acc, red, VL, RL, v0, rl, active, v, C, partial);
   }
 }
 
-// sums[c] = (s1, s2); accumulates dgamma += s2, dbeta += s1
-__global__ void bn_bwd_finalize(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ sums,
-                                float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per channel: sums[c] = (s1, s2); accumulates dgamma += s2, dbeta += s1
+__global__ void __launch_bounds__(256) bn_bwd_finalize(const float* __restrict__ partial, int nblocks, int C,
+                                                       float* __restrict__ sums, float* __restrict__ dgamma,
+                                                       float* __restrict__ dbeta) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= C) return;
-  double s = 0.0, t = 0.0;
-  for (int i = 0; i < nblocks; ++i) {
-    s += (double)partial[((int64_t)i * C + c) * 2];
-    t += (double)partial[((int64_t)i * C + c) * 2 + 1];
-  }
+  double s, t;
+  bn_sum_partials(partial, nblocks, C, c, s, t);
+  if ((threadIdx.x & 31) != 0) return;
   sums[2 * c] = (float)s, sums[2 * c + 1] = (float)t;
   dgamma[c] += (float)t;
   dbeta[c] += (float)s;
@@ -151,6 +227,16 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
     uint4 yv = make_uint4(0, 0, 0, 0);
     if (relu) yv = __ldg(y + i);
     const uint32_t du[4] = {dv.x, dv.y, dv.z, dv.w}, zu[4] = {zv.x, zv.y, zv.z, zv.w}, yu[4] = {yv.x, yv.y, yv.z, yv.w};
+    const float4 m0 = __ldg(reinterpret_cast<const float4*>(mean + c)), m1 = __ldg(reinterpret_cast<const float4*>(mean + c + 4));
+    const float4 i0 = __ldg(reinterpret_cast<const float4*>(invstd + c)), i1 = __ldg(reinterpret_cast<const float4*>(invstd + c + 4));
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(sums + 2 * c)), s1 = __ldg(reinterpret_cast<const float4*>(sums + 2 * c + 4));
+    const float4 s2 = __ldg(reinterpret_cast<const float4*>(sums + 2 * c + 8)), s3 = __ldg(reinterpret_cast<const float4*>(sums + 2 * c + 12));
+    const float mv[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    const float iv[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+    const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float sa[8] = {s0.x, s0.z, s1.x, s1.z, s2.x, s2.z, s3.x, s3.z};   // sum g
+    const float sb[8] = {s0.y, s0.w, s1.y, s1.w, s2.y, s2.w, s3.y, s3.w};   // sum g * xhat
     uint32_t o[4], go[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -160,10 +246,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
       float r[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int cc = c + 2 * k + e;
+        const int cc = 2 * k + e;
         if (relu && !(yy[e] > 0.f)) gg[e] = 0.f;
-        const float xhat = (zz[e] - __ldg(mean + cc)) * __ldg(invstd + cc);
-        r[e] = __ldg(gamma + cc) * __ldg(invstd + cc) * (gg[e] - __ldg(sums + 2 * cc) * inv_m - xhat * __ldg(sums + 2 * cc + 1) * inv_m);
+        const float xhat = (zz[e] - mv[cc]) * iv[cc];
+        r[e] = gv[cc] * iv[cc] * (gg[e] - sa[cc] * inv_m - xhat * sb[cc] * inv_m);
       }
       o[k] = pack_bf16x2(r[0], r[1]);
       go[k] = pack_bf16x2(gg[0], gg[1]);
@@ -374,17 +460,18 @@ static int grid_for(int64_t n, int per_thread = 1) {
   return (int)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
 }
 
-size_t bn_partial_bytes(int64_t M, int C) { return (size_t)ceil_div64(M, kBnRowsPerBlock) * C * 2 * sizeof(float); }
+size_t bn_partial_bytes(int64_t M, int C) { return (size_t)bn_blocks(M) * C * 2 * sizeof(float); }
 
 int bn_forward_train(const void* z, int64_t M, int C, const float* gamma, const float* beta, float eps, float momentum,
                      float* running_mean, float* running_var, float* save_mean, float* save_invstd, float* a, float* b,
                      float* partial, const void* residual, int relu, void* y, cudaStream_t stream) {
   NBC_REQUIRE(C % 8 == 0, "bn: C must be a multiple of 8");
-  const int nb = (int)ceil_div64(M, kBnRowsPerBlock);
-  bn_stats_partial<<<nb, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(z), M, C, partial);
+  const int nb = bn_blocks(M);
+  const int64_t rpb = ceil_div64(M, nb);
+  bn_stats_partial<<<nb, kBnThreads, 0, stream>>>(reinterpret_cast<const uint4*>(z), M, C, rpb, partial);
   NBC_CHECK_LAUNCH();
-  bn_stats_finalize<<<ceil_div(C, 128), 128, 0, stream>>>(partial, nb, C, M, gamma, beta, eps, momentum, running_mean,
-                                                          running_var, save_mean, save_invstd, a, b);
+  bn_stats_finalize<<<ceil_div(C, 8), 256, 0, stream>>>(partial, nb, C, M, gamma, beta, eps, momentum, running_mean,
+                                                        running_var, save_mean, save_invstd, a, b);
   NBC_CHECK_LAUNCH();
   const int64_t total8 = M * C / 8;
   bn_apply_kernel<<<grid_for(total8), 256, 0, stream>>>(reinterpret_cast<const uint4*>(z), a, b,
@@ -397,11 +484,14 @@ int bn_forward_train(const void* z, int64_t M, int C, const float* gamma, const 
 int bn_backward(const void* dy, const void* y, const void* z, int64_t M, int C, const float* gamma, const float* save_mean,
                 const float* save_invstd, int relu, float* partial, float* sums, float* dgamma, float* dbeta, void* dz,
                 void* g_out, cudaStream_t stream) {
-  const int nb = (int)ceil_div64(M, kBnRowsPerBlock);
-  bn_bwd_partial<<<nb, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(dy), reinterpret_cast<const uint32_t*>(y),
-                                         reinterpret_cast<const uint32_t*>(z), save_mean, save_invstd, M, C, relu, partial);
+  NBC_REQUIRE(C % 8 == 0, "bn: C must be a multiple of 8");
+  const int nb = bn_blocks(M);
+  const int64_t rpb = ceil_div64(M, nb);
+  bn_bwd_partial<<<nb, kBnThreads, 0, stream>>>(reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(y),
+                                                reinterpret_cast<const uint4*>(z), save_mean, save_invstd, M, C, relu, rpb,
+                                                partial);
   NBC_CHECK_LAUNCH();
-  bn_bwd_finalize<<<ceil_div(C, 128), 128, 0, stream>>>(partial, nb, C, sums, dgamma, dbeta);
+  bn_bwd_finalize<<<ceil_div(C, 8), 256, 0, stream>>>(partial, nb, C, sums, dgamma, dbeta);
   NBC_CHECK_LAUNCH();
   const int64_t total8 = M * C / 8;
   bn_bwd_apply_kernel<<<grid_for(total8), 256, 0, stream>>>(

@@ -11,53 +11,99 @@ static int grid_for2(int64_t n) {
   return (int)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
 }
 
-// ------------------------------------------------------------------------------------------------ maxpool backward
-// dx[n,h,w,c] = sum of dy over the (<= 4) 3x3/2 windows whose FIRST maximum (row-major scan, torch's rule) is (h,w).
-__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
-                                                          int N, int H, int W, int C, int Ho, int Wo,
-                                                          __nv_bfloat16* __restrict__ dx) {
-  const int64_t total = (int64_t)N * H * W * C;
+// ------------------------------------------------------------------------------------------------ maxpool (training)
+// Forward that also records, per output element, WHICH of the 9 window positions held the first maximum (row-major
+// scan, torch's rule); the backward then needs no comparisons: dx[h,w] = sum of dy over the (<= 4) windows whose
+// recorded position is (h,w).  One thread = 8 channels (16 bytes) of one pixel.
+__global__ void __launch_bounds__(256) maxpool_fwd_idx_kernel(const uint4* __restrict__ x, int N, int H, int W, int C8, int Ho,
+                                                              int Wo, uint4* __restrict__ y, uint2* __restrict__ idx) {
+  const int64_t total = (int64_t)N * Ho * Wo * C8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    int64_t t = i / C;
+    const int c = (int)(i % C8);
+    int64_t t = i / C8;
+    const int wo = (int)(t % Wo);
+    t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float best[8];
+    uint32_t pos[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) best[e] = -INFINITY, pos[e] = 0;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int h = 2 * ho - 1 + ky;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int w = 2 * wo - 1 + kx;
+        if (w < 0 || w >= W) continue;
+        const uint4 q = __ldg(x + (((int64_t)n * H + h) * W + w) * C8 + c);
+        const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float a = bf16lo(u[k]), b = bf16hi(u[k]);
+          if (a > best[2 * k]) best[2 * k] = a, pos[2 * k] = ky * 3 + kx;
+          if (b > best[2 * k + 1]) best[2 * k + 1] = b, pos[2 * k + 1] = ky * 3 + kx;
+        }
+      }
+    }
+    y[i] = make_uint4(pack_bf16x2(best[0], best[1]), pack_bf16x2(best[2], best[3]), pack_bf16x2(best[4], best[5]),
+                      pack_bf16x2(best[6], best[7]));
+    idx[i] = make_uint2(pos[0] | (pos[1] << 8) | (pos[2] << 16) | (pos[3] << 24),
+                        pos[4] | (pos[5] << 8) | (pos[6] << 16) | (pos[7] << 24));
+  }
+}
+
+__global__ void __launch_bounds__(256) maxpool_bwd_idx_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx, int N,
+                                                              int H, int W, int C8, int Ho, int Wo, uint4* __restrict__ dx) {
+  const int64_t total = (int64_t)N * H * W * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    int64_t t = i / C8;
     const int w = (int)(t % W);
     t /= W;
     const int h = (int)(t % H);
     const int n = (int)(t / H);
-    const __nv_bfloat16* xn = x + (int64_t)n * H * W * C + c;
-    const float v = __bfloat162float(xn[((int64_t)h * W + w) * C]);
-    float g = 0.f;
+    float g[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = 0.f;
     // windows (ho, wo) with 2*ho-1 <= h <= 2*ho+1
-    for (int ho = max(0, (h - 1 + 1) / 2); ho <= min(Ho - 1, (h + 1) / 2); ++ho) {
-      for (int wo = max(0, w / 2); wo <= min(Wo - 1, (w + 1) / 2); ++wo) {
-        // is (h, w) the first maximum of this window?
-        bool first = true;
-        for (int dy_ = -1; dy_ <= 1 && first; ++dy_) {
-          const int hh = 2 * ho + dy_;
-          if (hh < 0 || hh >= H) continue;
-          for (int dx_ = -1; dx_ <= 1; ++dx_) {
-            const int ww = 2 * wo + dx_;
-            if (ww < 0 || ww >= W) continue;
-            const float u = __bfloat162float(xn[((int64_t)hh * W + ww) * C]);
-            const bool before = (hh < h) || (hh == h && ww < w);
-            if (u > v || (before && u == v)) {
-              first = false;
-              break;
-            }
-          }
+    for (int ho = h / 2; ho <= min(Ho - 1, (h + 1) / 2); ++ho) {
+      const uint32_t ky = (uint32_t)(h - (2 * ho - 1));
+      for (int wo = w / 2; wo <= min(Wo - 1, (w + 1) / 2); ++wo) {
+        const uint32_t me = ky * 3 + (uint32_t)(w - (2 * wo - 1));
+        const int64_t o = (((int64_t)n * Ho + ho) * Wo + wo) * C8 + c;
+        const uint2 ix = __ldg(idx + o);
+        const uint4 q = __ldg(dy + o);
+        const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t word = k < 2 ? ix.x : ix.y;
+          const uint32_t p0 = (word >> (16 * (k & 1))) & 0xFFu, p1 = (word >> (16 * (k & 1) + 8)) & 0xFFu;
+          if (p0 == me) g[2 * k] += bf16lo(u[k]);
+          if (p1 == me) g[2 * k + 1] += bf16hi(u[k]);
         }
-        if (first) g += __bfloat162float(dy[(((int64_t)n * Ho + ho) * Wo + wo) * C + c]);
       }
     }
-    dx[i] = __float2bfloat16_rn(g);
+    dx[i] = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
   }
 }
 
-int maxpool_backward(const void* x, const void* dy, int N, int H, int W, int C, void* dx, cudaStream_t stream) {
+int maxpool_forward_idx(const void* x, int N, int H, int W, int C, void* y, void* idx, cudaStream_t stream) {
+  NBC_REQUIRE(C % 8 == 0, "maxpool: C must be a multiple of 8");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  maxpool_bwd_kernel<<<grid_for2((int64_t)N * H * W * C), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), N, H, W, C, Ho, Wo,
-      reinterpret_cast<__nv_bfloat16*>(dx));
+  maxpool_fwd_idx_kernel<<<grid_for2((int64_t)N * Ho * Wo * (C / 8)), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(x), N, H, W, C / 8, Ho, Wo, reinterpret_cast<uint4*>(y), reinterpret_cast<uint2*>(idx));
+  NBC_CHECK_LAUNCH();
+  return 0;
+}
+
+int maxpool_backward(const void* dy, const void* idx, int N, int H, int W, int C, void* dx, cudaStream_t stream) {
+  NBC_REQUIRE(C % 8 == 0, "maxpool: C must be a multiple of 8");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  maxpool_bwd_idx_kernel<<<grid_for2((int64_t)N * H * W * (C / 8)), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint2*>(idx), N, H, W, C / 8, Ho, Wo,
+      reinterpret_cast<uint4*>(dx));
   NBC_CHECK_LAUNCH();
   return 0;
 }

@@ -44,10 +44,11 @@ struct nbc_train_plan {
   int head_unit = -1;
   size_t cls_w_off = 0, cls_b_off = 0;  // floats
   size_t n_params = 0, n_stats = 0;
-  size_t padded_off, pool_off, drop_off, low_off, full_off, dfull_off, dlow_off, upws_off, gA_off, gB_off, gskip_off, dz_off,
+  size_t padded_off, pool_off, pidx_off, drop_off, low_off, full_off, dfull_off, dlow_off, upws_off, gA_off, gB_off, gskip_off, dz_off,
       d1_off, d2_off, up_off, partial_off, zeros_off, wce_off, ws_bytes;
   size_t big_bytes, small_bytes;
   void* prepared_ws = nullptr;
+  int wgrad_impl = 0;   // 0 = tcgen05 (wgrad_tc.cu), 1 = mma.sync / CUDA-core cross-check kernels
 };
 
 namespace nbc {
@@ -142,6 +143,7 @@ extern "C" nbc_train_plan* nbc_train_create(int N, int H, int W) {
   p->small_bytes = al(small * N * 2);
   p->padded_off = off, off += al(nbc_stem_tc_workspace_bytes(N, H, W));
   p->pool_off = off, off += al((size_t)N * p4 * 64 * 2);
+  p->pidx_off = off, off += al((size_t)N * p4 * 64);
   p->drop_off = off, off += al((size_t)N * p8 * 512 * 2);
   p->low_off = off, off += al((size_t)N * 3 * p8 * 4);
   p->full_off = off, off += al((size_t)N * 3 * H * W * 4);
@@ -296,9 +298,12 @@ static int unit_backward(const Ctx& c, Unit& u, const void* dy, int relu, void* 
   int rc = bn_backward(dy, c.ws + u.y_off, c.ws + u.z_off, M, u.Cout, c.params + u.g_off, c.st(u, 0), c.st(u, 1), relu,
                        c.partial(), c.st(u, 4), c.grads + u.g_off, c.grads + u.b_off, dz, g_out, c.stream);
   if (rc) return rc;
-  if (u.Cin == 3) return stem_wgrad(dz, c.ws + p->padded_off, p->N, u.Ho, u.Wo, c.grads + u.w_off, c.stream);
+  if (u.Cin == 3)
+    return c.p->wgrad_impl == 1 ? stem_wgrad(dz, c.ws + p->padded_off, p->N, u.Ho, u.Wo, c.grads + u.w_off, c.stream)
+                                : stem_wgrad_tc(dz, c.ws + p->padded_off, p->N, u.Ho, u.Wo, c.grads + u.w_off, c.stream);
   ConvGeom g{p->N, u.Hin, u.Win, u.Cin, u.Cout, u.k, u.k, u.stride, u.pad, u.dil, 0, 0};
-  rc = wgrad_mma(g, dz, c.ws + u.x_off, c.grads + u.w_off, c.stream);
+  rc = (c.p->wgrad_impl == 1 || !wgrad_tc_supported(g)) ? wgrad_mma(g, dz, c.ws + u.x_off, c.grads + u.w_off, c.stream)
+                                                         : wgrad_tc(g, dz, c.ws + u.x_off, c.grads + u.w_off, c.stream);
   if (rc) return rc;
   if (!u.need_dgrad) return 0;
   if (u.stride == 2) {
@@ -347,7 +352,7 @@ extern "C" int nbc_train_forward_backward(nbc_train_plan* p, float* params, floa
   if (rc) return rc;
   rc = unit_forward(c, stem, nullptr, 1);
   if (rc) return rc;
-  rc = nbc_maxpool3x3s2_bf16(ws + stem.y_off, N, p->H2, p->W2, 64, 0, ws + p->pool_off, stream);
+  rc = maxpool_forward_idx(ws + stem.y_off, N, p->H2, p->W2, 64, ws + p->pool_off, ws + p->pidx_off, stream);
   if (rc) return rc;
   for (TBlock& B : p->blocks) {
     Unit &u1 = p->units[B.c1], &u2 = p->units[B.c2], &u3 = p->units[B.c3];
@@ -401,7 +406,7 @@ extern "C" int nbc_train_forward_backward(nbc_train_plan* p, float* params, floa
   }
   // maxpool and stem
   const size_t g_pool = p->blocks[0].gout_off;
-  if ((rc = maxpool_backward(ws + stem.y_off, ws + g_pool, N, p->H2, p->W2, 64, ws + p->gskip_off, stream))) return rc;
+  if ((rc = maxpool_backward(ws + g_pool, ws + p->pidx_off, N, p->H2, p->W2, 64, ws + p->gskip_off, stream))) return rc;
   if ((rc = unit_backward(c, stem, ws + p->gskip_off, 1, nullptr))) return rc;
   return 0;
 }
@@ -426,6 +431,11 @@ extern "C" int64_t nbc_train_debug_offset(const nbc_train_plan* p, int what, int
     return (int64_t)(what == 3 ? p->full_off : p->dfull_off);
   }
   return -1;
+}
+extern "C" int nbc_train_set_wgrad_impl(nbc_train_plan* p, int impl) {
+  NBC_REQUIRE(p && (impl == 0 || impl == 1), "nbc_train_set_wgrad_impl: impl must be 0 (tcgen05) or 1 (mma.sync)");
+  p->wgrad_impl = impl;
+  return 0;
 }
 extern "C" int nbc_train_num_units(const nbc_train_plan* p) { return p ? (int)p->units.size() : 0; }
 

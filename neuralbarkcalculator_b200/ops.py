@@ -118,6 +118,28 @@ def conv_bf16(x, w_packed, bias, stride=1, pad=0, dil=1, relu=False, residual=No
     return y
 
 
+def conv_wgrad_bf16(dz, x, kh, kw, stride=1, pad=0, dil=1, impl=0, out=None):
+    """Weight gradient of conv_bf16: dz bf16 NHWC [N,Ho,Wo,Cout], x bf16 NHWC [N,H,W,Cin] -> f32 [Cout,kh,kw,Cin]
+    (accumulated into ``out`` when given).  impl 0 auto, 1 tcgen05, 2 mma.sync."""
+    lib = _lib.load()
+    dz = _contig(dz, torch.bfloat16, 'dz')
+    x = _contig(x, torch.bfloat16, 'x')
+    N, H, W, Cin = x.shape
+    Cout = dz.shape[3]
+    Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
+    if tuple(dz.shape) != (N, Ho, Wo, Cout):
+        raise RuntimeError('conv_wgrad_bf16: dz shape %s does not match the geometry %s' % (tuple(dz.shape), (N, Ho, Wo, Cout)))
+    with torch.cuda.device(x.device):
+        if out is None:
+            out = torch.zeros((Cout, kh, kw, Cin), dtype=torch.float32, device=x.device)
+        else:
+            out = _contig(out, torch.float32, 'out')
+        d = _lib.ConvDesc(N, H, W, Cin, Cout, kh, kw, stride, pad, dil, 0, impl, 0)
+        _lib.check(lib.nbc_conv_wgrad_bf16(C.byref(d), _ptr(dz), _ptr(x), _ptr(out), _stream(x.device)), 'nbc_conv_wgrad_bf16')
+    return out
+
+
 def stem_u8(img, mean, std, w_stem, bias):
     lib = _lib.load()
     img = _contig(img, torch.uint8, 'img')

@@ -169,6 +169,52 @@ def test_conv_tc_many_tiles(cuda_device):
     _conv_case(cuda_device, 64, 64, 3, 1, 1, N=2, H=96, W=256, relu=True, use_res=False, impl=1, seed=6)
 
 
+# ------------------------------------------------------------------------------------------------- weight gradient
+def _wgrad_case(dev, Cin, Cout, k, stride, dil, N, H, W, impl, seed=0):
+    """dW of one conv layer vs torch's own f32 conv weight gradient on the same bf16-rounded operands."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    pad = dil if k == 3 else 0
+    Ho = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    x = torch.randn(N, H, W, Cin, generator=g).to(torch.bfloat16)
+    dz = torch.randn(N, Ho, Wo, Cout, generator=g).to(torch.bfloat16)
+    got = ops.conv_wgrad_bf16(dz.to(dev), x.to(dev), k, k, stride=stride, pad=pad, dil=dil, impl=impl)
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (Cout, Cin, k, k), dz.float().permute(0, 3, 1, 2),
+                                      stride=stride, padding=pad, dilation=dil)          # OIHW
+    ref = ref.permute(0, 2, 3, 1)                                                          # [Cout][kh][kw][Cin]
+    err = (got.cpu() - ref).abs()
+    # exact products (bf16 x bf16 fits f32), f32 accumulation over N*Ho*Wo terms of unit variance in a different order
+    tol = 1e-4 * np.sqrt(N * Ho * Wo) + 1e-5 * ref.abs()
+    assert not (err > tol).any(), 'max err %.4g (ref rms %.4g) bad=%d of %d' % (err.max(), ref.pow(2).mean().sqrt(),
+                                                                             int((err > tol).sum()), err.numel())
+
+
+@pytest.mark.parametrize('impl', [1, 2])
+@pytest.mark.parametrize('shape', [(64, 64, 1, 1, 1), (64, 64, 3, 1, 1), (256, 64, 1, 1, 1), (64, 256, 1, 1, 1), (128, 128, 3, 2, 1),
+                                   (256, 512, 1, 2, 1), (128, 512, 1, 1, 1), (256, 256, 3, 1, 2), (512, 512, 3, 1, 4),
+                                   (1024, 256, 1, 1, 1), (2048, 512, 3, 1, 1)])
+def test_conv_wgrad(cuda_device, shape, impl):
+    Cin, Cout, k, stride, dil = shape
+    _wgrad_case(cuda_device, Cin, Cout, k, stride, dil, N=2, H=27, W=40, impl=impl)
+
+
+def test_conv_wgrad_tc_split_k(cuda_device):
+    # production-like geometry: 128-wide rows, many pixel tiles per CTA and several splits; accumulation into a
+    # non-zero buffer
+    ops = _ops()
+    _wgrad_case(cuda_device, 256, 256, 3, 1, 2, N=2, H=64, W=128, impl=1, seed=3)
+    _wgrad_case(cuda_device, 64, 64, 3, 1, 1, N=1, H=200, W=256, impl=1, seed=4)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(1, 16, 64, 128, generator=g).to(torch.bfloat16).to(cuda_device)
+    dz = torch.randn(1, 16, 64, 64, generator=g).to(torch.bfloat16).to(cuda_device)
+    base = torch.full((64, 1, 1, 128), 2.0, device=cuda_device)
+    a = ops.conv_wgrad_bf16(dz, x, 1, 1, impl=1)
+    b = ops.conv_wgrad_bf16(dz, x, 1, 1, impl=1, out=base.clone())
+    assert torch.allclose(b - 2.0, a, atol=1e-3)
+
+
 # ------------------------------------------------------------------------------------------------- stem / pool / head
 def test_stem_maxpool_head(cuda_device):
     ops = _ops()
