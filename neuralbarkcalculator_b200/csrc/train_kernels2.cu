@@ -239,27 +239,49 @@ __global__ void taps_table_kernel(int in_size, int out_size, float scale, int* _
 #pragma unroll
   for (int k = 0; k < 4; ++k) idx[4 * d + k] = ix[k], wt[4 * d + k] = w[k];
 }
-// out[r][j] = sum over candidates d of w(d,j) * in[r][d] along the LAST dim (rows = everything else)
-__global__ void __launch_bounds__(256) adjoint_last_kernel(const float* __restrict__ in, int64_t rows, int out_size /*hi-res*/,
-                                                           int in_size /*lo-res*/, float inv_scale, const int* __restrict__ idx,
-                                                           const float* __restrict__ wt, float* __restrict__ out) {
-  const int64_t total = rows * in_size;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int j = (int)(i % in_size);
-    const int64_t r = i / in_size;
-    int lo = (int)floorf(((float)j - 2.5f) * inv_scale) - 2, hi = (int)ceilf(((float)j + 2.5f) * inv_scale) + 2;
-    if (j == 0) lo = 0;
-    if (j == in_size - 1) hi = out_size - 1;
-    lo = max(lo, 0), hi = min(hi, out_size - 1);
-    const float* src = in + r * out_size;
-    float acc = 0.f;
-    for (int d = lo; d <= hi; ++d) {
-      const float v = __ldg(src + d);
+// Band table of the adjoint along one dimension: for low-res index j, band[j][t] = sum_k [idx(d,k) == j] * wt(d,k) with
+// d = lo[j] + t -- the (dense, short) column j of the interpolation matrix.  kAdjBand bounds the band length.
+constexpr int kAdjBand = 64;
+__global__ void adjoint_band_kernel(int in_size /*lo-res*/, int out_size /*hi-res*/, float inv_scale, const int* __restrict__ idx,
+                                    const float* __restrict__ wt, int* __restrict__ lo_out, float* __restrict__ band) {
+  const int j = blockIdx.x;
+  int lo = (int)floorf(((float)j - 2.5f) * inv_scale) - 2, hi = (int)ceilf(((float)j + 2.5f) * inv_scale) + 2;
+  if (j == 0) lo = 0;
+  if (j == in_size - 1) hi = out_size - 1;
+  lo = max(lo, 0), hi = min(hi, out_size - 1);
+  if (threadIdx.x == 0) lo_out[2 * j] = lo, lo_out[2 * j + 1] = hi - lo + 1;
+  for (int t = threadIdx.x; t < kAdjBand; t += blockDim.x) {
+    const int d = lo + t;
+    float a = 0.f;
+    if (d <= hi) {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (__ldg(idx + 4 * d + k) == j) acc = fmaf(__ldg(wt + 4 * d + k), v, acc);
+        if (idx[4 * d + k] == j) a += wt[4 * d + k];
     }
-    out[i] = acc;
+    band[j * kAdjBand + t] = a;
+  }
+}
+// out[r][j] = sum_t band[j][t] * in[r][lo[j] + t] along the LAST dim; one thread = one j for 4 consecutive rows
+__global__ void __launch_bounds__(256) adjoint_last_kernel(const float* __restrict__ in, int64_t rows, int out_size /*hi-res*/,
+                                                           int in_size /*lo-res*/, const int* __restrict__ lo_cnt,
+                                                           const float* __restrict__ band, float* __restrict__ out) {
+  const int64_t groups = (rows + 3) / 4;
+  const int64_t total = groups * in_size;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % in_size);
+    const int64_t r0 = (i / in_size) * 4;
+    const int lo = __ldg(lo_cnt + 2 * j), cnt = __ldg(lo_cnt + 2 * j + 1);
+    const float* bw = band + j * kAdjBand;
+    const float* src = in + r0 * out_size + lo;
+    const int nr = (int)min((int64_t)4, rows - r0);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < cnt; ++t) {
+      const float w = __ldg(bw + t);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < nr) acc[q] = fmaf(w, __ldg(src + (int64_t)q * out_size + t), acc[q]);
+    }
+    for (int q = 0; q < nr; ++q) out[(r0 + q) * in_size + j] = acc[q];
   }
 }
 // same along the second-to-last dim: in [R][H][w] -> out [R][h][w]
@@ -288,7 +310,8 @@ __global__ void __launch_bounds__(256) adjoint_rows_kernel(const float* __restri
   }
 }
 size_t upsample_bwd_workspace_bytes(int N, int C, int h, int w, int H, int W) {
-  return align_up((size_t)N * C * H * w * 4, 256) + align_up((size_t)(H + W) * 4 * 8, 256);
+  return align_up((size_t)N * C * H * w * 4, 256) + align_up((size_t)(H + W) * 4 * 8, 256) +
+         align_up((size_t)w * (kAdjBand + 2) * 4, 256);
 }
 int upsample_backward(const float* dup, int N, int C, int h, int w, int H, int W, float* dlow, void* workspace,
                       cudaStream_t stream) {
@@ -304,8 +327,14 @@ int upsample_backward(const float* dup, int N, int C, int h, int w, int H, int W
   NBC_CHECK_LAUNCH();
   taps_table_kernel<<<ceil_div(H, 128), 128, 0, stream>>>(h, H, sy, idx_y, wt_y);
   NBC_CHECK_LAUNCH();
-  adjoint_last_kernel<<<grid_for2((int64_t)N * C * H * w), 256, 0, stream>>>(dup, (int64_t)N * C * H, W, w, (float)W / (float)w,
-                                                                           idx_x, wt_x, T);
+  // the band of hi-res positions that touch one low-res column must fit the table
+  NBC_REQUIRE((int)ceilf(5.f * (float)W / (float)w) + 6 <= kAdjBand, "upsample_backward: scale %d/%d too large", W, w);
+  char* bt = tb + align_up((size_t)(H + W) * 4 * 8, 256);
+  int* lo_cnt = reinterpret_cast<int*>(bt);
+  float* band = reinterpret_cast<float*>(bt + (size_t)w * 8);
+  adjoint_band_kernel<<<w, 64, 0, stream>>>(w, W, (float)W / (float)w, idx_x, wt_x, lo_cnt, band);
+  NBC_CHECK_LAUNCH();
+  adjoint_last_kernel<<<grid_for2(((int64_t)N * C * H + 3) / 4 * w), 256, 0, stream>>>(dup, (int64_t)N * C * H, W, w, lo_cnt, band, T);
   NBC_CHECK_LAUNCH();
   adjoint_rows_kernel<<<grid_for2((int64_t)N * C * h * w), 256, 0, stream>>>(T, (int64_t)N * C, H, h, w, (float)H / (float)h,
                                                                            idx_y, wt_y, dlow);

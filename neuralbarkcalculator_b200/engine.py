@@ -45,7 +45,8 @@ class PredictEngine:
             self._ccl_ws = torch.empty(lib.nbc_ccl_workspace_bytes(self.chunk, Hc, Wo), dtype=torch.uint8, device=dev)
             hl = (((Hc - 1) // 2 + 1 - 1) // 2 + 1 - 1) // 2 + 1
             wl = (((Wo - 1) // 2 + 1 - 1) // 2 + 1 - 1) // 2 + 1
-            self._logits = torch.empty((self.chunk, 3, hl, wl), dtype=torch.float32, device=dev)
+            self._logits = [torch.empty((self.chunk, 3, hl, wl), dtype=torch.float32, device=dev) for _ in range(2)]
+            self._logits_free = [None, None]
             self._fl_host = torch.empty((n, 2), dtype=torch.int32).pin_memory()
 
     def _streams(self):
@@ -54,6 +55,7 @@ class PredictEngine:
             self._copy_stream = torch.cuda.Stream(dev)      # H2D of raw scans
             self._pre_stream = torch.cuda.Stream(dev)       # K1 (resize + trim)
             self._out_stream = torch.cuda.Stream(dev)       # D2H of masks
+            self._post_stream = torch.cuda.Stream(dev)      # K3 + K5 of the previous chunk, under the next network pass
             self._stage = [torch.empty(self.raw_size * self.raw_size * 3, dtype=torch.uint8, device=dev)
                            for _ in range(self.depth)]
             self._staged = [torch.cuda.Event() for _ in range(self.depth)]
@@ -68,19 +70,37 @@ class PredictEngine:
                                                 C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
                        'nbc_preprocess_4x_u8')
 
-    def _segment_chunk(self, a, b, exclude_nodes):
-        """Images a..b-1 as ONE ragged batch: network, K3 and K5 read the per-image heights on the device."""
+    def _segment_chunk(self, ci, a, b, exclude_nodes):
+        """Images a..b-1 as ONE ragged batch: network, K3 and K5 read the per-image heights on the device.  The network
+        runs on the main stream; K3 (upsample+argmax) and K5 (region removal + counts) follow on the post stream, so
+        they overlap the network pass of the next chunk (two logits buffers).  Returns the event that marks the chunk's
+        masks and counts as final."""
         plan = self.model.native_plan()
-        logits = plan.forward_ragged(self._proc[a:b], heights=self._heights[a:b], out=self._logits[:b - a])
-        ops.upsample_argmax_ragged(logits, self._heights[a:b], (self.raw_size // 4, self.out_w), out=self._masks[a:b])
-        ops.remove_small_zones_ragged(self._masks[a:b], self._heights[a:b], self.threshold, exclude_nodes,
-                                      workspace=self._ccl_ws, counts=self._counts[a:b])
+        main = torch.cuda.current_stream(self.device)
+        k = ci & 1
+        if self._logits_free[k] is not None:
+            main.wait_event(self._logits_free[k])        # K3 of chunk ci-2 has consumed this logits buffer
+        logits = plan.forward_ragged(self._proc[a:b], heights=self._heights[a:b], out=self._logits[k][:b - a])
+        net_done = torch.cuda.Event()
+        net_done.record(main)
+        done = torch.cuda.Event()
+        with torch.cuda.stream(self._post_stream):
+            self._post_stream.wait_event(net_done)
+            ops.upsample_argmax_ragged(logits, self._heights[a:b], (self.raw_size // 4, self.out_w), out=self._masks[a:b])
+            free = torch.cuda.Event()
+            free.record(self._post_stream)
+            self._logits_free[k] = free
+            ops.remove_small_zones_ragged(self._masks[a:b], self._heights[a:b], self.threshold, exclude_nodes,
+                                          workspace=self._ccl_ws, counts=self._counts[a:b])
+            done.record(self._post_stream)
+        return done
 
     def _run(self, n, get_raw, masks_host, bgr, bottom_up, exclude_nodes):
         """Software pipeline over chunks of images, with NO host synchronisation inside:
              copy stream : H2D of the raw scans (host path only), ``depth`` staging buffers
              pre stream  : K1 + heights for chunk c+1
-             main stream : ragged network + K3 + K5 for chunk c      out stream : D2H of finished masks"""
+             main stream : ragged network for chunk c                post stream: K3 + K5 for chunk c-1
+             out stream  : D2H of finished masks"""
         dev = self.device
         chunk, depth = self.chunk, self.depth
         with torch.cuda.device(dev):
@@ -89,8 +109,9 @@ class PredictEngine:
             main = torch.cuda.current_stream(dev)
             start = torch.cuda.Event()
             start.record(main)
-            for st in (self._copy_stream, self._pre_stream, self._out_stream):
+            for st in (self._copy_stream, self._pre_stream, self._out_stream, self._post_stream):
                 st.wait_event(start)
+            self._logits_free = [None, None]
             chunks = [(a, min(a + chunk, n)) for a in range(0, n, chunk)]
             pre_done = [torch.cuda.Event() for _ in chunks]
             issued = 0
@@ -116,10 +137,8 @@ class PredictEngine:
                     ops.heights_from_first_last(self._fl[a:b], out=self._heights[a:b])
                     pre_done[ci].record(self._pre_stream)
                 main.wait_event(pre_done[ci])
-                self._segment_chunk(a, b, exclude_nodes)
+                ev = self._segment_chunk(ci, a, b, exclude_nodes)
                 if masks_host is not None:
-                    ev = torch.cuda.Event()
-                    ev.record(main)
                     with torch.cuda.stream(self._out_stream):
                         self._out_stream.wait_event(ev)
                         for i in range(a, b):
@@ -127,6 +146,7 @@ class PredictEngine:
             with torch.cuda.stream(self._pre_stream):
                 self._fl_host[:n].copy_(self._fl[:n], non_blocking=True)
             main.wait_stream(self._pre_stream)
+            main.wait_stream(self._post_stream)
             main.wait_stream(self._out_stream)
 
     def rows(self, n):
