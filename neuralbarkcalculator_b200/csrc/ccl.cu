@@ -15,21 +15,24 @@ namespace nbc {
 
 // src[p] != 0 <=> pixel p belongs to the set being labelled.  Labels are indices into the whole [N,H,W] buffer
 // and always satisfy labels[p] <= p, -1 for pixels outside the set.
-// vh (optional): ragged batch, image n has vh[n] valid rows of the H-row canvas; pixels below are outside the image
-__device__ __forceinline__ bool row_valid(int64_t p, int H, int W, const int* vh) {
-  if (vh == nullptr) return true;
-  const int64_t r = p / W;
-  return (int)(r % H) < __ldg(vh + (int)(r / H));
-}
+// vh (optional): ragged batch, image n has vh[n] valid rows of the H-row canvas; pixels below are outside the image.
+// Every kernel runs on a (pixel blocks, image) grid; a block that starts below the last valid row of its image
+// exits at once, so the dead part of a ragged canvas costs nothing and is never read or written.
+__device__ __forceinline__ int valid_rows(int n, int H, const int* vh) { return vh == nullptr ? H : min(H, __ldg(vh + n)); }
 
-__global__ void __launch_bounds__(256) ccl_init(const uint8_t* __restrict__ src, int H, int W, int64_t total,
-                                                int* __restrict__ labels, int* __restrict__ sizes,
-                                                const int* __restrict__ vh) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) ccl_init(const uint8_t* __restrict__ src, int H, int W, int* __restrict__ labels,
+                                                int* __restrict__ sizes, const int* __restrict__ vh) {
+  const int n = blockIdx.y;
+  const int64_t HW = (int64_t)H * W;
+  const int64_t live = (int64_t)valid_rows(n, H, vh) * W;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x;
+  if (i0 >= live) return;   // block-uniform
+  const int64_t i = i0 + threadIdx.x;
+  const int64_t p = (int64_t)n * HW + i;
   const int lane = threadIdx.x & 31;
-  const bool inb = p < total;
-  const bool in = inb && row_valid(p, H, W, vh) && src[p] != 0;
-  const int x = inb ? (int)(p % W) : 0;
+  const bool inb = i < live;
+  const bool in = inb && src[p] != 0;
+  const int x = inb ? (int)(i % W) : 0;
   const unsigned m = __ballot_sync(0xffffffffu, in);
   const unsigned rowstart = __ballot_sync(0xffffffffu, x == 0);
   // link[k] = lanes k and k-1 are both in the set and in the same image row
@@ -70,32 +73,52 @@ __device__ __forceinline__ void unite(int* labels, int a, int b) {
   } while (!done);
 }
 
-__global__ void __launch_bounds__(256) ccl_merge(const uint8_t* __restrict__ src, int H, int W, int64_t total,
-                                                 int* __restrict__ labels) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= total || labels[p] < 0) return;   // labels < 0: not in the set (or outside a ragged image)
+// Row-to-row unions.  Pixels of a horizontal run are already equivalent (ccl_init inside a warp, the lane-0 union
+// below across warp boundaries), so a union with the row above is only needed ONCE per pair of touching runs: at
+// the first pixel where the pair starts to touch.  With l = left, u = up, ul = up-left, ur = up-right:
+//   u in set : unite(p, u) unless (l and ul are in the set)   -- then l made the same union (l~p, ul~u by runs)
+//   u not    : unite(p, ul) unless l is in the set            -- then l united with ul (its own "up")
+//              unite(p, ur) unless r is in the set            -- then r unites with ur (its own "up")
+// which turns ~one union per pixel into ~one per touching run pair.
+__global__ void __launch_bounds__(256) ccl_merge(const uint8_t* __restrict__ src, int H, int W, int* __restrict__ labels,
+                                                 const int* __restrict__ vh) {
+  const int n = blockIdx.y;
+  const int64_t HW = (int64_t)H * W;
+  const int64_t live = (int64_t)valid_rows(n, H, vh) * W;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= live) return;
+  const int64_t p = (int64_t)n * HW + i;
+  if (src[p] == 0) return;
   const int lane = threadIdx.x & 31;
-  const int x = (int)(p % W);
-  const int y = (int)((p / W) % H);
+  const int x = (int)(i % W);
+  const int y = (int)(i / W);
   const int ip = (int)p;
-  if (x > 0 && lane == 0 && src[p - 1]) unite(labels, ip, ip - 1);  // run cut by the warp boundary
+  const bool l = x > 0 && src[p - 1] != 0;
+  if (l && lane == 0) unite(labels, ip, ip - 1);  // run cut by the warp boundary
   if (y > 0) {
     const int64_t up = p - W;
+    const bool ul = x > 0 && src[up - 1] != 0;
     if (src[up]) {
-      unite(labels, ip, (int)up);
+      if (!(l && ul)) unite(labels, ip, (int)up);
     } else {
-      if (x > 0 && src[up - 1]) unite(labels, ip, (int)up - 1);
-      if (x < W - 1 && src[up + 1]) unite(labels, ip, (int)up + 1);
+      if (ul && !l) unite(labels, ip, (int)up - 1);
+      if (x < W - 1 && src[up + 1] != 0 && src[p + 1] == 0) unite(labels, ip, (int)up + 1);
     }
   }
 }
 
-__global__ void __launch_bounds__(256) ccl_flatten_count(int64_t total, int threshold, int* __restrict__ labels,
-                                                         int* __restrict__ sizes) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) ccl_flatten_count(int H, int W, int threshold, int* __restrict__ labels,
+                                                         int* __restrict__ sizes, const int* __restrict__ vh) {
+  const int n = blockIdx.y;
+  const int64_t HW = (int64_t)H * W;
+  const int64_t live = (int64_t)valid_rows(n, H, vh) * W;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x;
+  if (i0 >= live) return;   // block-uniform
+  const int64_t i = i0 + threadIdx.x;
+  const int64_t p = (int64_t)n * HW + i;
   const int lane = threadIdx.x & 31;
   int root = -1;
-  if (p < total && labels[p] >= 0) {
+  if (i < live && labels[p] >= 0) {
     root = find_root(labels, (int)p);
     labels[p] = root;
   }
@@ -112,30 +135,34 @@ __global__ void __launch_bounds__(256) ccl_flatten_count(int64_t total, int thre
 
 // stage A result: setB[p] = background after removing small foreground components
 __global__ void __launch_bounds__(256) ccl_stage_a_apply(const uint8_t* __restrict__ mask, const int* __restrict__ labels,
-                                                         const int* __restrict__ sizes, int threshold, int64_t total,
+                                                         const int* __restrict__ sizes, int threshold,
                                                          uint8_t* __restrict__ setB, int H, int W,
                                                          const int* __restrict__ vh) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= total) return;
-  if (!row_valid(p, H, W, vh)) {
-    setB[p] = 0;
-    return;
-  }
+  const int n = blockIdx.y;
+  const int64_t HW = (int64_t)H * W;
+  const int64_t live = (int64_t)valid_rows(n, H, vh) * W;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= live) return;
+  const int64_t p = (int64_t)n * HW + i;
   const bool bg = (mask[p] == 0) || (__ldcg(sizes + labels[p]) < threshold);
   setB[p] = bg ? 1 : 0;
 }
 
 __global__ void __launch_bounds__(256) ccl_final(uint8_t* __restrict__ mask, const uint8_t* __restrict__ setB,
                                                  const int* __restrict__ labels, const int* __restrict__ sizes,
-                                                 int threshold, int exclude_nodes, int64_t HW,
-                                                 int* __restrict__ counts, int W, const int* __restrict__ vh) {
+                                                 int threshold, int exclude_nodes, int H, int W,
+                                                 int* __restrict__ counts, const int* __restrict__ vh) {
   __shared__ int s_cnt[3];
+  const int n = blockIdx.y;
+  const int64_t HW = (int64_t)H * W;
+  const int64_t live = (int64_t)valid_rows(n, H, vh) * W;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x;
+  if (i0 >= live) return;   // block-uniform
   if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
   __syncthreads();
-  const int n = blockIdx.y;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = i0 + threadIdx.x;
   int cls = -1;
-  if (i < HW && (vh == nullptr || (int)(i / W) < __ldg(vh + n))) {
+  if (i < live) {
     const int64_t p = (int64_t)n * HW + i;
     const uint8_t m = mask[p];
     const bool bg = setB[p] && (__ldcg(sizes + labels[p]) >= threshold);
@@ -176,27 +203,26 @@ static int remove_small_zones_impl(uint8_t* mask, int N, int H, int W, int thres
   int* labels = reinterpret_cast<int*>(ws);
   int* sizes = reinterpret_cast<int*>(ws + align_up((size_t)total * 4, 256));
   uint8_t* setB = reinterpret_cast<uint8_t*>(ws + 2 * align_up((size_t)total * 4, 256));
-  const unsigned blocks = (unsigned)ceil_div64(total, 256);
+  const int64_t HW = (int64_t)H * W;
+  const dim3 grid((unsigned)ceil_div64(HW, 256), N);
   NBC_CUDA(cudaMemsetAsync(counts, 0, (size_t)N * 3 * sizeof(int32_t), stream));
   // stage A: foreground components
-  ccl_init<<<blocks, 256, 0, stream>>>(mask, H, W, total, labels, sizes, vh);
+  ccl_init<<<grid, 256, 0, stream>>>(mask, H, W, labels, sizes, vh);
   NBC_CHECK_LAUNCH();
-  ccl_merge<<<blocks, 256, 0, stream>>>(mask, H, W, total, labels);
+  ccl_merge<<<grid, 256, 0, stream>>>(mask, H, W, labels, vh);
   NBC_CHECK_LAUNCH();
-  ccl_flatten_count<<<blocks, 256, 0, stream>>>(total, threshold, labels, sizes);
+  ccl_flatten_count<<<grid, 256, 0, stream>>>(H, W, threshold, labels, sizes, vh);
   NBC_CHECK_LAUNCH();
-  ccl_stage_a_apply<<<blocks, 256, 0, stream>>>(mask, labels, sizes, threshold, total, setB, H, W, vh);
+  ccl_stage_a_apply<<<grid, 256, 0, stream>>>(mask, labels, sizes, threshold, setB, H, W, vh);
   NBC_CHECK_LAUNCH();
   // stage B: background components of the stage-A result
-  ccl_init<<<blocks, 256, 0, stream>>>(setB, H, W, total, labels, sizes, nullptr);
+  ccl_init<<<grid, 256, 0, stream>>>(setB, H, W, labels, sizes, vh);
   NBC_CHECK_LAUNCH();
-  ccl_merge<<<blocks, 256, 0, stream>>>(setB, H, W, total, labels);
+  ccl_merge<<<grid, 256, 0, stream>>>(setB, H, W, labels, vh);
   NBC_CHECK_LAUNCH();
-  ccl_flatten_count<<<blocks, 256, 0, stream>>>(total, threshold, labels, sizes);
+  ccl_flatten_count<<<grid, 256, 0, stream>>>(H, W, threshold, labels, sizes, vh);
   NBC_CHECK_LAUNCH();
-  const int64_t HW = (int64_t)H * W;
-  dim3 grid((unsigned)ceil_div64(HW, 256), N);
-  ccl_final<<<grid, 256, 0, stream>>>(mask, setB, labels, sizes, threshold, exclude_nodes, HW, counts, W, vh);
+  ccl_final<<<grid, 256, 0, stream>>>(mask, setB, labels, sizes, threshold, exclude_nodes, H, W, counts, vh);
   NBC_CHECK_LAUNCH();
   return 0;
 }

@@ -105,9 +105,17 @@ __global__ void __launch_bounds__(256) resize4x_pass1(const uint8_t* __restrict_
     mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     nondark += __shfl_xor_sync(0xffffffffu, nondark, o);
   }
-  if ((threadIdx.x & 31) == 0) {
-    atomicMax(&hdr->inv_min, 255 - mn);
-    atomicMax(&hdr->max, mx);
+  // one (min, max, count) per block; the two range atomics all land on the same address, so they are skipped when
+  // they cannot change it (the values only grow, a stale read just means one redundant atomic)
+  __shared__ int s_mn[8], s_mx[8], s_nd[8];
+  const int wid = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) s_mn[wid] = mn, s_mx[wid] = mx, s_nd[wid] = nondark;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int i = 1; i < nw; ++i) mn = min(mn, s_mn[i]), mx = max(mx, s_mx[i]), nondark += s_nd[i];
+    if (255 - mn > __ldcg(&hdr->inv_min)) atomicMax(&hdr->inv_min, 255 - mn);
+    if (mx > __ldcg(&hdr->max)) atomicMax(&hdr->max, mx);
     if (nondark) atomicAdd(&rowcount[ho], nondark);
   }
 }
