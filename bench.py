@@ -141,6 +141,23 @@ def time_reference(steps, warmup, sd):
     return len(times) / sum(times), times
 
 
+def time_reference_train(sd, hw=512):
+    """CPU oracle training step (plain torch f32: train(), forward, weighted CE, backward, Adam -- the reference's
+    __main__.py:231-269 step) on a bounded sample: ONE hw x hw crop (the reference trains on 512 crops, __main__.py:159),
+    scaled to 1024^2-image units by the pixel ratio."""
+    from oracle import synth, train as otrain, model as omodel
+    torch.set_num_threads(os.cpu_count())
+    x = omodel.normalise_u8(synth.texture_u8(hw, hw, 3))
+    t = torch.from_numpy(synth.class_mask(hw, hw, 4)).long().unsqueeze(0)
+    otrain.train_step(sd, x, t, dropout=0.8)          # warm-up
+    t0 = time.perf_counter()
+    otrain.train_step(sd, x, t, dropout=0.8)
+    dt = time.perf_counter() - t0
+    scale = (hw * hw) / (1024.0 * 1024.0)
+    return scale / dt, ('1 timed step (after 1 warm-up) of the CPU oracle on one %dx%d crop, batch 1, all host threads; '
+                        'value scaled to 1024^2 images by the pixel ratio %.3f' % (hw, hw, scale))
+
+
 def main():
     args = parse()
     rank = int(os.environ.get('RANK', 0))
@@ -154,6 +171,15 @@ def main():
 
     if args.impl == 'reference':
         if rank != 0:
+            return
+        if args.workload == 'train':
+            v, sample = time_reference_train(sd)
+            print(json.dumps({'impl': 'reference', 'metric': 'images/sec (training step)', 'value': v, 'unit': 'images/s',
+                              'n_gpus': args.gpus, 'steps': 1, 'warmup': 1, 'ms_per_step': 1000.0 / v, 'higher_is_better': True,
+                              'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                              'config': {'workload': 'training step (configs[3])', 'sample': sample},
+                              'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': sample},
+                              'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
             return
         v, times = time_reference(args.steps, args.warmup, sd)
         line = {'impl': 'reference', 'metric': 'images/sec', 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus,
@@ -213,10 +239,11 @@ def main():
         from oracle import synth
         from neuralbarkcalculator_b200.train import Trainer
         B = args.batch or 8
-        imgs = torch.from_numpy(np.stack([synth.texture_u8(1024, 1024, 100 * rank + i) for i in range(2)])).to(dev)
-        imgs = imgs.repeat((B + 1) // 2, 1, 1, 1)[:B].contiguous()
-        tgt = torch.from_numpy(np.stack([synth.class_mask(1024, 1024, 200 * rank + i) for i in range(2)])).to(dev)
-        tgt = tgt.repeat((B + 1) // 2, 1, 1)[:B].contiguous()
+        imgs_h = torch.from_numpy(np.stack([synth.texture_u8(1024, 1024, 100 * rank + i) for i in range(2)]))
+        imgs_h = imgs_h.repeat((B + 1) // 2, 1, 1, 1)[:B].contiguous().pin_memory()
+        tgt_h = torch.from_numpy(np.stack([synth.class_mask(1024, 1024, 200 * rank + i) for i in range(2)]))
+        tgt_h = tgt_h.repeat((B + 1) // 2, 1, 1)[:B].contiguous().pin_memory()
+        imgs, tgt = imgs_h.to(dev), tgt_h.to(dev)
         tr = Trainer(sd, B, 1024, 1024, device=str(dev), dropout=0.8)
         res = {}
 
@@ -226,15 +253,40 @@ def main():
         sampler.start()
         ms, launches = timed(step, args.steps, args.warmup)
         clocks = sampler.summary()
+        # end to end: this step's images and targets come from pinned host memory, the loss is read back every step
+        imgs_d, tgt_d = torch.empty_like(imgs), torch.empty_like(tgt)
+
+        def step_host():
+            imgs_d.copy_(imgs_h, non_blocking=True)
+            tgt_d.copy_(tgt_h, non_blocking=True)
+            res['loss_host'] = float(tr.step(imgs_d, tgt_d).item())
+        ms_h, _ = timed(step_host, args.steps, max(1, args.warmup))
         if rank == 0:
+            # algorithmic FLOPs of the convolutions of one step: forward + data gradient + weight gradient
+            # (2*MAC; 1106.64 GFLOP forward per 1024^2 image; the stem has no data gradient)
+            step_flops = (3 * 1106.64e9 - 4.93e9) * B
+            achieved = step_flops * args.steps / (ms / 1000.0) / 1e12
+            cpu_base = None
+            if not args.no_cpu_baseline and world == 1:
+                v, sample = time_reference_train(sd)
+                cpu_base = {'value': v, 'unit': 'images/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': sample}
             line = {'metric': 'images/sec (training step)', 'value': world * B * args.steps / (ms / 1000.0), 'unit': 'images/s',
                     'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
                     'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
                     'config': {'workload': 'training step: FCN-ResNet50 3-class, max-of-index weighted CE, batch %d per GPU at '
                                            '1024x1024, Adam lr 5e-4 wd 2e-3, dropout 0.8, NCCL all-reduce of the flat gradient '
-                                           'buffer (configs[3])' % B, 'parallelism': 'dp%d' % world},
+                                           'buffer (configs[3])' % B, 'parallelism': 'dp%d' % world,
+                               'l2': 'activations of one step (tens of GB) are far larger than L2; no flush needed'},
                     'clocks': clocks, 'gpu_launches': launches, 'loss': float(res['loss']),
-                    'tflops': 3 * 1106.64e9 * B * args.steps / (ms / 1000.0) / 1e12, 'e2e': None, 'roofline': None, 'cpu_baseline': None}
+                    'e2e': {'value': world * B * args.steps / (ms_h / 1000.0), 'unit': 'images/s',
+                            'h2d_bytes_per_step': int(imgs_h.numel() + tgt_h.numel()), 'd2h_bytes_per_step': 4,
+                            'ms_per_step': ms_h / args.steps},
+                    'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': tf_peak, 'unit': 'TFLOP/s',
+                                 'frac': achieved / tf_peak, 'traffic': None, 'peak_kind': peak_kind + ' (sustained bf16)',
+                                 'kernel': 'conv_tc_kernel (forward + data gradient) and wgrad_tc_kernel: algorithmic conv FLOPs of '
+                                           'the step / WHOLE step time (BatchNorm, loss, Adam and the all-reduce included), i.e. a '
+                                           'lower bound on the kernels\' own rate'},
+                    'cpu_baseline': cpu_base}
             print(json.dumps(line))
         if world > 1:
             dist.destroy_process_group()
@@ -312,15 +364,18 @@ def main():
         conv_ms, conv_fl = sum(m for m, _ in conv), sum(f for _, f in conv)
         tot_ms = sum(m for m, _ in layers)
         achieved = conv_fl / (conv_ms * 1e-3) / 1e12
-        traffic = None
+        traffic, tensor_pct = None, None
         tp = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')     # dram bytes per launch from the committed ncu capture
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get('conv_tc_dram_bytes_per_launch')
+            tj = json.load(open(tp))
+            traffic = tj.get('conv_tc_dram_bytes_per_launch')
+            tensor_pct = tj.get('conv_tc_tensor_pipe_active_pct_time_weighted')
         roof = {'bound': 'tensor', 'achieved': achieved, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf_peak,
                 'traffic': traffic, 'peak_kind': peak_kind + ' (sustained bf16)',
                 'kernel': 'conv_tc_kernel: the 53 tensor-core conv launches of one network pass over a chunk of %d scans '
                           '(dense [%d,624,1024,3] batch = mean trimmed height), per-launch CUDA events, median of 3; '
                           'achieved = sum of algorithmic FLOPs / sum of launch durations' % (chunk, chunk),
+                'tensor_pipe_active_pct_ncu': tensor_pct,      # time-weighted over the same 53 launches (profiles/r01i_*)
                 'flops_per_launch_avg': conv_fl / len(conv), 'ms_per_launch_avg': conv_ms / len(conv),
                 'conv_share_of_forward': conv_ms / tot_ms, 'forward_ms_per_image': tot_ms / chunk}
         if not args.no_cpu_baseline and world == 1:
