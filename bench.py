@@ -75,6 +75,7 @@ class ClockSampler(threading.Thread):
 
     def summary(self):
         self.stop_flag = True
+        self.join(timeout=8)      # a query that started inside the timed region still counts (nvidia-smi takes ~0.1-0.3 s)
         sm, mx, reasons = [], 0.0, set()
         for r in self.rows:
             try:
