@@ -137,6 +137,23 @@ size_t nbc_wce_workspace_bytes(int N, int H, int W);
 int nbc_wce_fwd_bwd(const float* logits, const void* target, int target_is_i64, const float* weights3, int N, int H,
                     int W, float* loss, float* grad, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- N1: Lovasz-Softmax loss, forward + backward  (lovasz_losses.py:19-31, 162-218; the loss of __main__.py:239) --
+ * logits f32 planar [N,3,H,W]; target u8 or int64 [N,H,W] (labels 0..2); classes='present', per_image=False.
+ * loss: device scalar; grad (may be NULL): upstream * d loss / d logits, f32 [N,3,H,W].  The per-class descending
+ * sort is cub::DeviceRadixSort; everything else (fused softmax + errors, Lovasz gradient, softmax backward) is ours. */
+size_t nbc_lovasz_workspace_bytes(int N, int H, int W);
+int nbc_lovasz_softmax_fwd_bwd(const float* logits, const void* target, int target_is_i64, int N, int H, int W,
+                               float upstream, float* loss, float* grad, void* workspace, size_t workspace_bytes,
+                               void* stream);
+
+/* ---- N2: validation metrics  (lovasz_losses.py:54-77 iou / miou; utils.py:201-235 PixelWiseF1) ------------------
+ * nbc_argmax3_u8: torch.argmax(logits, 1) of f32 planar [N,3,H,W] (ties -> lowest index) as u8 [N,H,W].
+ * nbc_confusion_matrix: cm9[t*3+p] = number of pixels with label t and prediction p (device uint64[9], overwritten);
+ * IoU_c = cm[c][c] / (row_c + col_c - cm[c][c]), F1_c = 2 cm[c][c] / (row_c + col_c) follow on the host. */
+int nbc_argmax3_u8(const float* logits, int N, int H, int W, uint8_t* out, void* stream);
+int nbc_confusion_matrix(const uint8_t* pred, const void* target, int target_is_i64, int64_t n_pixels, uint64_t* cm9,
+                         void* stream);
+
 /* ---- the whole network  (models.py:27-43 SimpleSegmentationModel.forward, 127-139 fcn_resnet50) ------------------
  * tensors_host: host array of DEVICE pointers to the 326 f32 state_dict tensors in torchvision key order
  * (backbone.conv1.weight, backbone.bn1.{weight,bias,running_mean,running_var,num_batches_tracked}, ...).
@@ -195,6 +212,9 @@ int64_t nbc_train_debug_offset(const nbc_train_plan* plan, int what, int index, 
 int nbc_train_num_units(const nbc_train_plan* plan);
 /* weight-gradient kernels used by the plan: 0 = tcgen05 (default), 1 = mma.sync / CUDA-core cross-check kernels */
 int nbc_train_set_wgrad_impl(nbc_train_plan* plan, int impl);
+/* loss of the step: 0 = CustomWeightedCrossEntropy (utils.py:151-165, default), 1 = LovaszSoftmax (__main__.py:239),
+ * 2 = MixedLoss = CE / 4 + Lovasz (utils.py:185-192) */
+int nbc_train_set_loss(nbc_train_plan* plan, int kind);
 int nbc_train_adam(float* params, const float* grads, float* adam_m, float* adam_v, int64_t n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 

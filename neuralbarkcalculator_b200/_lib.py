@@ -43,6 +43,11 @@ SIGNATURES = {
                                       c_void_p]),
     'nbc_wce_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'nbc_wce_fwd_bwd': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'nbc_lovasz_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'nbc_lovasz_softmax_fwd_bwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                                   c_size_t, c_void_p]),
+    'nbc_argmax3_u8': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'nbc_confusion_matrix': (c_int, [c_void_p, c_void_p, c_int, c_i64, c_void_p, c_void_p]),
     'nbc_plan_create': (c_void_p, [C.POINTER(c_void_p), c_int, C.POINTER(c_float), C.POINTER(c_float), c_int]),
     'nbc_plan_destroy': (None, [c_void_p]),
     'nbc_plan_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int]),
@@ -64,6 +69,7 @@ SIGNATURES = {
     'nbc_train_debug_offset': (c_i64, [c_void_p, c_int, c_int, C.POINTER(C.c_int32)]),
     'nbc_train_num_units': (c_int, [c_void_p]),
     'nbc_train_set_wgrad_impl': (c_int, [c_void_p, c_int]),
+    'nbc_train_set_loss': (c_int, [c_void_p, c_int]),
     'nbc_train_adam': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float, c_float,
                        c_int, c_float, c_void_p]),
 }

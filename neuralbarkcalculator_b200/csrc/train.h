@@ -38,6 +38,8 @@ size_t upsample_bwd_workspace_bytes(int N, int C, int h, int w, int H, int W);
 int upsample_backward(const float* dup, int N, int C, int h, int w, int H, int W, float* dlow, void* workspace,
                       cudaStream_t stream);
 int zero_insert(const void* dz, int N, int Ho, int Wo, int H, int W, int C, void* up, cudaStream_t stream);
+// out = sa * a + sb * b (lovasz.cu)
+int axpby(const float* a, float sa, const float* b, float sb, int64_t n, float* out, cudaStream_t stream);
 int adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float wd,
               int step, float grad_scale, cudaStream_t stream);
 

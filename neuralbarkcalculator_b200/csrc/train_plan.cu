@@ -49,6 +49,8 @@ struct nbc_train_plan {
   size_t big_bytes, small_bytes;
   void* prepared_ws = nullptr;
   int wgrad_impl = 0;   // 0 = tcgen05 (wgrad_tc.cu), 1 = mma.sync / CUDA-core cross-check kernels
+  int loss_kind = 0;    // 0 = weighted CE, 1 = Lovasz-Softmax, 2 = CE / 4 + Lovasz
+  size_t lov_off = 0, dfull2_off = 0, loss2_off = 0;
 };
 
 namespace nbc {
@@ -160,6 +162,9 @@ extern "C" nbc_train_plan* nbc_train_create(int N, int H, int W) {
   p->partial_off = off, off += al(bn_partial_bytes((int64_t)N * p2, 2048));
   p->zeros_off = off, off += al(2048 * 4);
   p->wce_off = off, off += al(nbc_wce_workspace_bytes(N, H, W));
+  p->lov_off = off, off += al(nbc_lovasz_workspace_bytes(N, H, W));
+  p->dfull2_off = off, off += al((size_t)N * 3 * H * W * 4);
+  p->loss2_off = off, off += al(16);
   p->ws_bytes = off;
 
   // ---- static data flow: inputs of the units, gradient ping-pong of the blocks ----------------------------------
@@ -380,9 +385,27 @@ extern "C" int nbc_train_forward_backward(nbc_train_plan* p, float* params, floa
   float* dlow = reinterpret_cast<float*>(ws + p->dlow_off);
   if ((rc = head_1x1(cls_in, P8, N, 512, params + p->cls_w_off, params + p->cls_b_off, low, 0, stream))) return rc;
   if ((rc = nbc_upsample_bicubic(low, N, 3, p->H8, p->W8, H, W, full, stream))) return rc;
-  if ((rc = nbc_wce_fwd_bwd(full, target, 0, weights3, N, H, W, loss, dfull, ws + p->wce_off, nbc_wce_workspace_bytes(N, H, W),
-                            stream)))
-    return rc;
+  if (p->loss_kind == 0) {
+    if ((rc = nbc_wce_fwd_bwd(full, target, 0, weights3, N, H, W, loss, dfull, ws + p->wce_off, nbc_wce_workspace_bytes(N, H, W),
+                              stream)))
+      return rc;
+  } else if (p->loss_kind == 1) {
+    if ((rc = nbc_lovasz_softmax_fwd_bwd(full, target, 0, N, H, W, 1.f, loss, dfull, ws + p->lov_off,
+                                         nbc_lovasz_workspace_bytes(N, H, W), stream)))
+      return rc;
+  } else {
+    // MixedLoss (utils.py:185-192): CE / 4 + Lovasz, for the value and for the gradient
+    float* dfull2 = reinterpret_cast<float*>(ws + p->dfull2_off);
+    float* loss2 = reinterpret_cast<float*>(ws + p->loss2_off);
+    if ((rc = nbc_wce_fwd_bwd(full, target, 0, weights3, N, H, W, loss2, dfull2, ws + p->wce_off, nbc_wce_workspace_bytes(N, H, W),
+                              stream)))
+      return rc;
+    if ((rc = nbc_lovasz_softmax_fwd_bwd(full, target, 0, N, H, W, 1.f, loss2 + 1, dfull, ws + p->lov_off,
+                                         nbc_lovasz_workspace_bytes(N, H, W), stream)))
+      return rc;
+    if ((rc = axpby(dfull2, 0.25f, dfull, 1.f, (int64_t)N * 3 * H * W, dfull, stream))) return rc;
+    if ((rc = axpby(loss2, 0.25f, loss2 + 1, 1.f, 1, loss, stream))) return rc;
+  }
 
   // ---- backward -----------------------------------------------------------------------------------------------
   if ((rc = upsample_backward(dfull, N, 3, p->H8, p->W8, H, W, dlow, ws + p->upws_off, stream))) return rc;
@@ -435,6 +458,11 @@ extern "C" int64_t nbc_train_debug_offset(const nbc_train_plan* p, int what, int
 extern "C" int nbc_train_set_wgrad_impl(nbc_train_plan* p, int impl) {
   NBC_REQUIRE(p && (impl == 0 || impl == 1), "nbc_train_set_wgrad_impl: impl must be 0 (tcgen05) or 1 (mma.sync)");
   p->wgrad_impl = impl;
+  return 0;
+}
+extern "C" int nbc_train_set_loss(nbc_train_plan* p, int kind) {
+  NBC_REQUIRE(p && kind >= 0 && kind <= 2, "nbc_train_set_loss: kind must be 0 (weighted CE), 1 (Lovasz) or 2 (mixed)");
+  p->loss_kind = kind;
   return 0;
 }
 extern "C" int nbc_train_num_units(const nbc_train_plan* p) { return p ? (int)p->units.size() : 0; }

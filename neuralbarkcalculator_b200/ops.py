@@ -330,6 +330,56 @@ def wce_fwd_bwd(logits, target, weights, need_grad=True):
     return loss, grad
 
 
+def lovasz_softmax_fwd_bwd(logits, target, need_grad=True, upstream=1.0):
+    """N1: LovaszSoftmax (lovasz_losses.py:162-218) on f32 logits [N,3,H,W] and u8|int64 labels [N,H,W] ->
+    (loss 0-dim f32, grad f32 [N,3,H,W] or None)."""
+    lib = _lib.load()
+    logits = _contig(logits, torch.float32, 'logits')
+    _dev(target, 'target')
+    if target.dtype not in (torch.uint8, torch.int64):
+        raise RuntimeError('lovasz_softmax_fwd_bwd: target must be uint8 or int64')
+    target = target.contiguous()
+    N, Cc, H, W = logits.shape
+    if Cc != 3 or tuple(target.shape) != (N, H, W):
+        raise RuntimeError('lovasz_softmax_fwd_bwd: logits [N,3,H,W] and target [N,H,W] expected')
+    with torch.cuda.device(logits.device):
+        loss = torch.zeros((), dtype=torch.float32, device=logits.device)
+        grad = torch.empty_like(logits) if need_grad else None
+        ws = torch.empty(lib.nbc_lovasz_workspace_bytes(N, H, W), dtype=torch.uint8, device=logits.device)
+        _lib.check(lib.nbc_lovasz_softmax_fwd_bwd(_ptr(logits), _ptr(target), 1 if target.dtype == torch.int64 else 0, N, H, W,
+                                                  C.c_float(upstream), _ptr(loss), _ptr(grad), _ptr(ws), ws.numel(),
+                                                  _stream(logits.device)), 'nbc_lovasz_softmax_fwd_bwd')
+    return loss, grad
+
+
+def argmax3_u8(logits):
+    """torch.argmax(logits, 1) of f32 [N,3,H,W] as u8 [N,H,W]."""
+    lib = _lib.load()
+    logits = _contig(logits, torch.float32, 'logits')
+    N, Cc, H, W = logits.shape
+    if Cc != 3:
+        raise RuntimeError('argmax3_u8: 3 classes expected')
+    with torch.cuda.device(logits.device):
+        out = torch.empty((N, H, W), dtype=torch.uint8, device=logits.device)
+        _lib.check(lib.nbc_argmax3_u8(_ptr(logits), N, H, W, _ptr(out), _stream(logits.device)), 'nbc_argmax3_u8')
+    return out
+
+
+def confusion_matrix(pred_u8, target):
+    """N2: cm[t, p] (int64 CUDA tensor [3,3]) over all pixels of pred u8 [...] and target u8|int64 of the same shape."""
+    lib = _lib.load()
+    pred_u8 = _contig(pred_u8, torch.uint8, 'pred')
+    _dev(target, 'target')
+    if target.dtype not in (torch.uint8, torch.int64) or target.numel() != pred_u8.numel():
+        raise RuntimeError('confusion_matrix: target must be uint8 or int64 with as many elements as pred')
+    target = target.contiguous()
+    with torch.cuda.device(pred_u8.device):
+        cm = torch.zeros(9, dtype=torch.int64, device=pred_u8.device)
+        _lib.check(lib.nbc_confusion_matrix(_ptr(pred_u8), _ptr(target), 1 if target.dtype == torch.int64 else 0,
+                                            pred_u8.numel(), _ptr(cm), _stream(pred_u8.device)), 'nbc_confusion_matrix')
+    return cm.view(3, 3)
+
+
 # ---- the network plan ---------------------------------------------------------------------------------------------
 class Plan:
     """Owns an nbc_plan (BN-folded bf16 weights on the device) built from the 326 state_dict tensors."""

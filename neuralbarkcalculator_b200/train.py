@@ -16,7 +16,8 @@ from .utils import get_pos_weight
 
 class Trainer:
     def __init__(self, state_dict, N, H, W, device='cuda:0', lr=5e-4, weight_decay=2e-3, betas=(0.9, 0.999), eps=1e-8,
-                 dropout=0.8, class_weights=None, mean=(0.7399, 0.6139, 0.4401), std=(0.1068, 0.1272, 0.1271)):
+                 dropout=0.8, class_weights=None, mean=(0.7399, 0.6139, 0.4401), std=(0.1068, 0.1272, 0.1271),
+                 loss='weighted_ce'):
         self.lib = _lib.load()
         self.device = torch.device(device)
         _lib.require_device(self.device.index if self.device.index is not None else torch.cuda.current_device())
@@ -33,6 +34,10 @@ class Trainer:
             if not self.handle:
                 raise RuntimeError('nbc_train_create failed: ' + _lib.last_error())
             h = C.c_void_p(self.handle)
+            kinds = {'weighted_ce': 0, 'lovasz': 1, 'mixed': 2}   # utils.py:151-165 / __main__.py:239 / utils.py:185-192
+            if loss not in kinds:
+                raise ValueError("loss must be 'weighted_ce', 'lovasz' or 'mixed'")
+            _lib.check(self.lib.nbc_train_set_loss(h, kinds[loss]), 'nbc_train_set_loss')
             n = self.lib.nbc_train_param_count(h)
             self.params = torch.zeros(n, dtype=torch.float32, device=self.device)
             self.grads = torch.zeros(n, dtype=torch.float32, device=self.device)

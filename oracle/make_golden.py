@@ -172,6 +172,36 @@ def main():
               indent=1)
 
     # ---- stats strings (models.py:323-332): reference arithmetic is inline in _predict_images, restated -------------
+    # ---- N1 / N2: Lovasz-Softmax loss (+ gradient), MixedLoss, iou / miou -- the reference's own lovasz_losses module ----
+    import lovasz_losses as ref_lovasz
+    from oracle import lovasz as olovasz
+    g = torch.Generator().manual_seed(8)
+    lv_logits = torch.randn(2, 3, 24, 40, generator=g) * 2.0
+    lv_target = torch.from_numpy(np.stack([synth.class_mask(24, 40, s) for s in (5, 6)])).long()
+    p = lv_logits.clone().requires_grad_(True)
+    ref_l = ref_lovasz.LovaszSoftmax()(p, lv_target)
+    ref_l.backward()
+    ora_l, ora_g = olovasz.lovasz_softmax_with_grad(lv_logits, lv_target)
+    assert float(ref_l) == float(ora_l) and torch.equal(p.grad, ora_g), 'Lovasz oracle differs from the reference'
+    two = lv_target.clone()
+    two[two == 2] = 1                                   # a batch without class 2: classes='present' drops it
+    ref_l2 = ref_lovasz.LovaszSoftmax()(lv_logits, two)
+    ora_l2, ora_g2 = olovasz.lovasz_softmax_with_grad(lv_logits, two)
+    assert float(ref_l2) == float(ora_l2)
+    ref_iou = ref_lovasz.iou(lv_logits, lv_target)
+    assert np.array_equal(ref_iou, olovasz.iou(lv_logits, lv_target)) and ref_lovasz.miou(lv_logits, lv_target) == olovasz.miou(lv_logits, lv_target)
+    w = torch.tensor(olosses.DEFAULT_WEIGHTS)
+    ref_mixed = ref_utils.MixedLoss(w)(lv_logits, lv_target) if hasattr(ref_utils, 'MixedLoss') else None
+    ora_mixed = olovasz.mixed_loss(lv_logits, lv_target, w)
+    if ref_mixed is not None:
+        assert float(ref_mixed) == float(ora_mixed), 'MixedLoss oracle differs from the reference'
+    np.savez_compressed(os.path.join(OUT, 'lovasz_small.npz'), logits=lv_logits.numpy(), target=lv_target.numpy().astype(np.uint8),
+                        loss=np.float32(ora_l), grad=ora_g.numpy(), loss_two_classes=np.float32(ora_l2), grad_two_classes=ora_g2.numpy(),
+                        iou=ref_iou, mixed=np.float32(ora_mixed),
+                        confusion=olovasz.confusion_matrix(torch.argmax(lv_logits, 1).numpy(), lv_target.numpy()))
+    report.append('lovasz: LovaszSoftmax loss %.8f and gradient bit-identical to reference lovasz_losses.LovaszSoftmax; '
+                  'iou/miou identical; MixedLoss %s' % (float(ora_l), 'identical to reference utils.MixedLoss' if ref_mixed is not None else 'not importable'))
+
     m = synth.class_mask(611, 1024, 9)
     np.savez_compressed(os.path.join(OUT, 'stats_small.npz'), mask=m, strings=np.array(opost.class_stats_strings(m)))
 

@@ -20,7 +20,8 @@ def _simulate_bf16(net):
             m.register_forward_hook(rnd)
 
 
-def train_step(state_dict, x, target, weights=None, dropout=0.0, lr=5e-4, weight_decay=2e-3, steps=1, bf16_sim=False):
+def train_step(state_dict, x, target, weights=None, dropout=0.0, lr=5e-4, weight_decay=2e-3, steps=1, bf16_sim=False,
+               loss_kind='weighted_ce'):
     """x: f32 [N,3,H,W] normalised; target: int64 [N,H,W].  Returns dict(loss, grads {name: tensor}, state_dict).
 
     bf16_sim=True reproduces the storage precision of the B200 path inside the torch oracle (see _simulate_bf16): a
@@ -44,7 +45,14 @@ def train_step(state_dict, x, target, weights=None, dropout=0.0, lr=5e-4, weight
                     if p_.dim() == 4 and not n_.startswith('classifier.4'):
                         p_.data = p_.data.bfloat16().float()   # weights as the tensor cores see them (master copy not kept: 1 step)
         logits = net(x)
-        loss = losses.custom_weighted_cross_entropy(logits, target, w)
+        if loss_kind == 'weighted_ce':      # utils.py:151-165 (north_star's loss)
+            loss = losses.custom_weighted_cross_entropy(logits, target, w)
+        elif loss_kind == 'lovasz':         # __main__.py:239, the loss main() really uses
+            from . import lovasz
+            loss = lovasz.lovasz_softmax(logits, target)
+        else:                               # utils.py:185-192 MixedLoss
+            from . import lovasz
+            loss = lovasz.mixed_loss(logits, target, w)
         loss.backward()
         out['loss'] = float(loss)
         out['grads'] = {k: p.grad.detach().clone() for k, p in net.named_parameters()}

@@ -19,6 +19,11 @@ pytestmark = pytest.mark.gpu
 IMPLS = [int(v) for v in os.environ.get('NBC_TEST_IMPLS', '2,1').split(',')]   # 1 = tcgen05, 2 = mma.sync
 
 
+def _synth():
+    from oracle import synth
+    return synth
+
+
 def _ops():
     from neuralbarkcalculator_b200 import ops
     return ops
@@ -383,3 +388,71 @@ def test_wce_large_vs_oracle(cuda_device):
     loss, grad = ops.wce_fwd_bwd(logits.to(cuda_device), target.to(torch.uint8).to(cuda_device), w.to(cuda_device))
     assert abs(float(loss) - float(ref_loss)) < 2e-5 * abs(float(ref_loss))
     assert (grad.cpu() - ref_grad).abs().max() < 1e-9 + 2e-5 * ref_grad.abs().max()
+
+
+# ------------------------------------------------------------------------------------------------- N1 Lovasz / N2 metrics
+def _lovasz_check(dev, logits, target, ref_loss, ref_grad, target_dtype=torch.uint8):
+    ops = _ops()
+    loss, grad = ops.lovasz_softmax_fwd_bwd(logits.to(dev), target.to(target_dtype).to(dev))
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(ref_loss)) < 2e-6 + 1e-5 * abs(float(ref_loss)), (float(loss), float(ref_loss))
+    gerr = (grad.cpu() - ref_grad).abs().max()
+    # the gradient at a pixel is its Lovasz weight at its rank (a difference of two Jaccard values, computed with the
+    # reference's own f32 expression) through the softmax Jacobian: agreement to f32 round-off
+    assert gerr < 1e-8 + 2e-5 * float(ref_grad.abs().max()), (float(gerr), float(ref_grad.abs().max()))
+
+
+def test_lovasz_golden(cuda_device, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'lovasz_small.npz'))
+    logits, target = torch.from_numpy(g['logits']), torch.from_numpy(g['target'])
+    _lovasz_check(cuda_device, logits, target, g['loss'], torch.from_numpy(g['grad']))
+    _lovasz_check(cuda_device, logits, target, g['loss'], torch.from_numpy(g['grad']), torch.int64)
+    two = target.clone()
+    two[two == 2] = 1       # class 2 absent: classes='present' drops it from the mean
+    _lovasz_check(cuda_device, logits, two, g['loss_two_classes'], torch.from_numpy(g['grad_two_classes']))
+
+
+def test_lovasz_large_vs_oracle(cuda_device):
+    from oracle import lovasz as olovasz
+    g = torch.Generator().manual_seed(21)
+    logits = torch.randn(3, 3, 200, 333, generator=g) * 2.5
+    target = torch.from_numpy(np.stack([_synth().class_mask(200, 333, s) for s in (1, 2, 3)])).long()
+    loss, grad = olovasz.lovasz_softmax_with_grad(logits, target)
+    _lovasz_check(cuda_device, logits, target, loss, grad)
+    # autograd wrapper + MixedLoss mirror (utils.py:185-192)
+    from neuralbarkcalculator_b200 import utils as nutils
+    from oracle import losses as olosses
+    w = torch.tensor(olosses.DEFAULT_WEIGHTS)
+    p = logits.to(cuda_device).requires_grad_(True)
+    out = nutils.MixedLoss(w)(p, target.to(cuda_device))
+    out.backward()
+    ref = logits.clone().requires_grad_(True)
+    ref_out = olovasz.mixed_loss(ref, target, w)
+    ref_out.backward()
+    assert abs(float(out) - float(ref_out)) < 1e-5 * abs(float(ref_out)) + 1e-6
+    assert (p.grad.cpu() - ref.grad).abs().max() < 1e-8 + 2e-5 * float(ref.grad.abs().max())
+
+
+def test_metrics_vs_oracle(cuda_device, golden_dir):
+    from oracle import lovasz as olovasz
+    from neuralbarkcalculator_b200 import lovasz_losses as nl, utils as nutils
+    ops = _ops()
+    g = np.load(os.path.join(golden_dir, 'lovasz_small.npz'))
+    logits, target = torch.from_numpy(g['logits']), torch.from_numpy(g['target']).long()
+    cm = ops.confusion_matrix(ops.argmax3_u8(logits.to(cuda_device)), target.to(cuda_device))
+    assert np.array_equal(cm.cpu().numpy(), g['confusion'])
+    assert np.array_equal(nl.iou(logits.to(cuda_device), target.to(cuda_device)), g['iou'])
+    assert nl.miou(logits.to(cuda_device), target.to(cuda_device)) == np.mean(g['iou'])
+    # ties resolve to the lowest index, like torch.argmax
+    tie = torch.zeros(1, 3, 4, 4)
+    tie[0, 1, 0, 0] = tie[0, 2, 0, 0] = 1.0
+    am = ops.argmax3_u8(tie.to(cuda_device)).cpu()
+    assert am[0, 0, 0] == 1 and int(am.sum()) == 1
+    # PixelWiseF1 on a larger batch (argmax -> per-image region removal -> F1), every class_to_watch flavour
+    gen = torch.Generator().manual_seed(4)
+    big = torch.nn.functional.interpolate(torch.randn(2, 3, 20, 30, generator=gen), size=(160, 240), mode='bilinear') * 3
+    lab = torch.from_numpy(np.stack([_synth().class_mask(160, 240, s) for s in (7, 8)])).long()
+    for watch in (None, 'loss', 1, 'all'):
+        ours = nutils.PixelWiseF1(watch)(big.to(cuda_device), lab.to(cuda_device))
+        ref = olovasz.pixelwise_f1(big, lab, watch)
+        assert np.allclose(ours, ref, rtol=0, atol=1e-12), (watch, ours, ref)

@@ -167,3 +167,30 @@ def test_train_dropout_and_determinism(cuda_device, synthetic_sd):
         last = float(tr2.step(xi, ti))
     print('\nloss over 8 steps on a fixed batch: %.4f -> %.4f' % (first, last))
     assert last < first
+
+
+@pytest.mark.parametrize('loss_kind', ['lovasz', 'mixed'])
+def test_train_step_lovasz_and_mixed(cuda_device, synthetic_sd, loss_kind):
+    """The step with the loss the reference's main() really uses (LovaszSoftmax, __main__.py:239) and with MixedLoss
+    (utils.py:185-192), on the tamed network (see test_train_gradients_strict_on_tamed_network): loss and every
+    gradient against the f32 oracle."""
+    from neuralbarkcalculator_b200.train import Trainer
+    sd = {k: v.clone() for k, v in synthetic_sd.items()}
+    for k in sd:
+        if k.endswith('bn3.weight'):
+            sd[k] *= 0.05
+    N, H, W = 2, 64, 96
+    imgs, tgt, x = _batch(N, H, W, seed=3)
+    wt = torch.ones(3)
+    ref = otrain.train_step(sd, x, torch.from_numpy(tgt).long(), weights=wt, dropout=0.0, loss_kind=loss_kind)
+    tr = Trainer(sd, N, H, W, device='cuda:0', dropout=0.0, class_weights=wt, loss=loss_kind)
+    loss = float(tr.forward_backward(torch.from_numpy(imgs).to(cuda_device), torch.from_numpy(tgt).to(cuda_device)))
+    print('\n[%s] loss ours %.5f f32 oracle %.5f' % (loss_kind, loss, ref['loss']))
+    assert abs(loss - ref['loss']) < 0.01 * abs(ref['loss'])
+    grads = tr.gradients()
+    worst = sorted((_cos(grads[k].cpu(), g32), float(grads[k].cpu().norm() / (g32.norm() + 1e-30)), k) for k, g32 in ref['grads'].items())
+    for c, r, k in worst[:5]:
+        print('[%s] lowest cos: %-45s cos %.4f norm ratio %.3f' % (loss_kind, k, c, r))
+    assert worst[0][0] > 0.9, worst[0]
+    assert np.median([c for c, _, _ in worst]) > 0.97
+    assert all(0.9 < r < 1.1 for _, r, _ in worst), [t for t in worst if not 0.9 < t[1] < 1.1]

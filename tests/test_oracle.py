@@ -155,3 +155,41 @@ def test_bmp_roundtrip(tmp_path):
     p = str(tmp_path / 'a.bmp')
     synth.write_bmp(p, img)
     assert np.array_equal(opipe.load_rgb(p), img)
+
+
+# ------------------------------------------------------------------------------------------------- N1 / N2 (next rows)
+def test_lovasz_oracle_matches_golden(golden_dir):
+    """oracle/lovasz.py reproduces the values make_golden.py pinned against the reference's own lovasz_losses module."""
+    from oracle import lovasz as olovasz
+    g = np.load(os.path.join(golden_dir, 'lovasz_small.npz'))
+    logits, target = torch.from_numpy(g['logits']), torch.from_numpy(g['target']).long()
+    loss, grad = olovasz.lovasz_softmax_with_grad(logits, target)
+    assert float(loss) == float(g['loss']) and np.array_equal(grad.numpy(), g['grad'])
+    two = target.clone()
+    two[two == 2] = 1
+    loss2, grad2 = olovasz.lovasz_softmax_with_grad(logits, two)
+    assert float(loss2) == float(g['loss_two_classes']) and np.array_equal(grad2.numpy(), g['grad_two_classes'])
+    assert np.array_equal(olovasz.iou(logits, target), g['iou'])
+    assert np.array_equal(olovasz.confusion_matrix(torch.argmax(logits, 1).numpy(), target.numpy()), g['confusion'])
+    from oracle import losses as olosses
+    assert float(olovasz.mixed_loss(logits, target, torch.tensor(olosses.DEFAULT_WEIGHTS))) == float(g['mixed'])
+
+
+def test_lovasz_oracle_properties():
+    from oracle import lovasz as olovasz
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(1, 3, 16, 16, generator=g)
+    target = torch.randint(0, 3, (1, 16, 16), generator=g)
+    # perfect, confident predictions -> loss ~ 0; the loss is bounded by 1; gradient sums to ~0 over the classes
+    perfect = torch.nn.functional.one_hot(target, 3).permute(0, 3, 1, 2).float() * 40.0
+    assert float(olovasz.lovasz_softmax(perfect, target)) < 1e-6
+    loss, grad = olovasz.lovasz_softmax_with_grad(logits, target)
+    assert 0.0 < float(loss) <= 1.0 and float(grad.sum(1).abs().max()) < 1e-6
+    # F1 from the confusion matrix == sklearn, including the "absent class takes the mean of the others" rule
+    from sklearn.metrics import f1_score
+    pred = torch.randint(0, 2, (1, 16, 16), generator=g).numpy()
+    lab = torch.randint(0, 2, (1, 16, 16), generator=g).numpy()
+    cm = olovasz.confusion_matrix(pred, lab)
+    sk = f1_score(lab.reshape(-1), pred.reshape(-1), labels=[0, 1, 2], average=None, zero_division=0)
+    sk[2] = np.delete(sk, 2).mean()
+    assert np.allclose(olovasz.f1_from_confusion(cm), sk)
