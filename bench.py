@@ -38,7 +38,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='predict64', choices=['predict64', 'batch32', 'train'])
+    ap.add_argument('--workload', default='predict64', choices=['predict64', 'batch32', 'train', 'cli'])
     ap.add_argument('--batch', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
@@ -291,6 +291,51 @@ def main():
             print(json.dumps(line))
         if world > 1:
             dist.destroy_process_group()
+        return
+
+    if args.workload == 'cli':
+        # BASELINE.json configs[1] literally: `predict.py ROOT --exclude_nodes` on a folder of 64 synthetic 4096^2 BMPs
+        # (files on tmpfs), every output file written.  Wall clock: file reads and PNG encoding are host work.
+        import argparse as _ap
+        import shutil
+        import tempfile
+        from oracle import synth
+        from neuralbarkcalculator_b200 import predict as npredict
+        B = args.batch or BATCH
+        if os.environ.get('NBC_DEBUG_HANG'):      # all thread stacks after N seconds, then exit (debugging aid)
+            import faulthandler
+            faulthandler.dump_traceback_later(int(os.environ['NBC_DEBUG_HANG']), exit=True)
+        base = '/dev/shm' if os.path.isdir('/dev/shm') else None
+        root = tempfile.mkdtemp(prefix='nbc_cli_', dir=base)
+        try:
+            synth.make_raw_folder(root, B, size=RAW, pool=min(B, 8), seed0=500)
+            ns = _ap.Namespace(root_path=root, device=str(dev), exclude_nodes=True, only_preprocess=False)
+            times = []
+            for it in range(args.warmup + args.steps):
+                shutil.rmtree(os.path.join(root, 'processed'), ignore_errors=True)
+                shutil.rmtree(os.path.join(root, 'results'), ignore_errors=True)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                rows = npredict.main(ns, state_dict=sd)
+                torch.cuda.synchronize()
+                if it >= args.warmup:
+                    times.append(time.perf_counter() - t0)
+            n_files = sum(len(f) for _, _, f in os.walk(os.path.join(root, 'results'))) + sum(len(f) for _, _, f in os.walk(os.path.join(root, 'processed')))
+        finally:
+            shutil.rmtree(root, ignore_errors=True)
+        if rank == 0:
+            v = B * len(times) / sum(times)
+            print(json.dumps({'metric': 'images/sec (predict.py CLI, files in, files out)', 'value': v, 'unit': 'images/s', 'n_gpus': 1,
+                              'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * sum(times) / len(times),
+                              'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+                              'config': {'workload': 'predict.py ROOT --exclude_nodes on %d synthetic 4096x4096 24-bit BMPs on tmpfs: '
+                                                     'BMP read, K1, FCN-ResNet50, K3, K5, processed + dual PNG encode, CSV (configs[1]); '
+                                                     'includes model construction and weight packing each step' % B,
+                                         'timing': 'wall clock around predict.main(); %d files written per step' % n_files,
+                                         'host_cores': os.cpu_count()},
+                              'gpu_launches': _lib.launch_count(), 'e2e': {'value': v, 'unit': 'images/s',
+                              'h2d_bytes_per_step': B * RAW * RAW * 3, 'd2h_bytes_per_step': B * 4 * 1024 * 1024},
+                              'roofline': None, 'cpu_baseline': None, 'rows': len(rows)}))
         return
 
     if args.workload == 'batch32':

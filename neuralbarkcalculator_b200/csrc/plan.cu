@@ -50,6 +50,8 @@ struct nbc_plan {
   float* cls_w = nullptr;  // f32 [3][512]
   float* cls_b = nullptr;
   std::vector<void*> allocs;
+  char* slab = nullptr;       // parameter slab (see dev_alloc)
+  size_t slab_used = 0;
   int impl = 0;
   int f16 = 0;   // 16-bit storage format: 0 bf16 (default), 1 fp16
   // cached launch lists (tensor maps are encoded once per shape / workspace): key = (N, H, W, workspace, impl)
@@ -60,7 +62,22 @@ struct nbc_plan {
 
 namespace nbc {
 
+// Parameters are carved out of one slab (one cudaMalloc / cudaFree per plan instead of ~115: cudaFree synchronises the
+// device and unmaps memory, which made tearing a plan down take up to a second); an allocation that does not fit --
+// never for FCN-ResNet50, 66 MB of packed weights -- falls back to its own cudaMalloc.
+constexpr size_t kPlanSlabBytes = 96u << 20;
 static int dev_alloc(nbc_plan* p, void** ptr, size_t bytes) {
+  if (p->slab == nullptr) {
+    NBC_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->slab), kPlanSlabBytes));
+    p->allocs.push_back(p->slab);
+    p->slab_used = 0;
+  }
+  const size_t need = align_up(bytes, 256);
+  if (p->slab_used + need <= kPlanSlabBytes) {
+    *ptr = p->slab + p->slab_used;
+    p->slab_used += need;
+    return 0;
+  }
   NBC_CUDA(cudaMalloc(ptr, bytes));
   p->allocs.push_back(*ptr);
   return 0;

@@ -28,6 +28,7 @@ class _Slot:
         self.counts = torch.empty((n, 3), dtype=torch.int32, device=dev)
         self.fl_host = torch.empty((n, 2), dtype=torch.int32).pin_memory()
         self.counts_host = torch.empty((n, 3), dtype=torch.int32).pin_memory()
+        self.proc_host = None     # pinned copies of the processed canvases (folder pipeline only)
         self.done = None          # event: every consumer of this slot's buffers has finished
         self.pending = False      # a submitted batch in this slot has not been collected yet
 
@@ -125,7 +126,7 @@ class PredictEngine:
             done.record(self._post_stream)
         return done
 
-    def _run(self, n, get_raw, masks_host, bgr, bottom_up, exclude_nodes, on_device):
+    def _run(self, n, get_raw, masks_host, bgr, bottom_up, exclude_nodes, on_device, want_processed=False, only_preprocess=False):
         """Software pipeline over chunks of images, with NO host synchronisation inside:
              copy stream : H2D of the raw scans (host path only), ``depth`` staging buffers
              pre stream  : K1 + heights for chunk c+1
@@ -170,6 +171,14 @@ class PredictEngine:
                 with torch.cuda.stream(self._pre_stream):
                     ops.heights_from_first_last(slot.fl[a:b], out=slot.heights[a:b])
                     pre_done.record(self._pre_stream)
+                if want_processed:
+                    if slot.proc_host is None:
+                        slot.proc_host = torch.empty(slot.proc.shape, dtype=torch.uint8).pin_memory()
+                    with torch.cuda.stream(self._out_stream):
+                        self._out_stream.wait_event(pre_done)
+                        slot.proc_host[a:b].copy_(slot.proc[a:b], non_blocking=True)
+                if only_preprocess:
+                    continue
                 main.wait_event(pre_done)
                 ev = self._segment_chunk(slot, a, b, exclude_nodes)
                 if masks_host is not None:
@@ -198,11 +207,14 @@ class PredictEngine:
         return slot.counts[:n], slot.masks[:n], slot.heights[:n]
 
     # -- end to end from pinned host memory --------------------------------------------------------------------------
-    def submit_host(self, raws_host, masks_host=None, bgr=True, bottom_up=True, exclude_nodes=False):
+    def submit_host(self, raws_host, masks_host=None, bgr=True, bottom_up=True, exclude_nodes=False, want_processed=False,
+                    only_preprocess=False):
         """Enqueue one batch of pinned u8 CPU tensors (raw pixel arrays) and return a ticket at once; at most two
-        tickets may be outstanding.  ``collect`` waits for it."""
+        tickets may be outstanding.  ``collect`` waits for it.  want_processed: also copy the processed (resized +
+        trimmed) images back (``ticket.slot.proc_host[i, :rows[i]]`` after collect); only_preprocess: stop after K1."""
         n = len(raws_host)
-        slot = self._run(n, lambda i: raws_host[i], masks_host, bgr, bottom_up, exclude_nodes, False)
+        slot = self._run(n, lambda i: raws_host[i], masks_host, bgr, bottom_up, exclude_nodes, False, want_processed,
+                         only_preprocess)
         slot.pending = True
         return Ticket(slot, n, masks_host)
 

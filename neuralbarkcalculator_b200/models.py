@@ -190,15 +190,17 @@ class NeuralBarkCalculator():
     DEFAULT_MM_PER_PIXEL = 3.6 * 3.6
 
     def __init__(self, model_path, device, mean=DEFAULT_MEAN, std=DEFAULT_STD, target_size=1024,
-                 mm_per_pix=DEFAULT_MM_PER_PIXEL, state_dict=None, precision='bf16'):
+                 mm_per_pix=DEFAULT_MM_PER_PIXEL, state_dict=None, precision='bf16', load_weights=True):
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise RuntimeError("device '%s': this build runs on CUDA (B200) only -- no CPU path" % device)
-        self.model = fcn_resnet50(pretrained=False)
-        if state_dict is None:
-            state_dict = torch.load(model_path, map_location=self.device)
-        self.model.load_state_dict(state_dict)
-        self.model.to(self.device)
+        with torch.device('meta'):      # no random init: every parameter is replaced by the checkpoint's tensor below
+            self.model = fcn_resnet50(pretrained=False)
+        if load_weights:      # --only_preprocess never touches the network (predict.py:55-58)
+            if state_dict is None:
+                state_dict = torch.load(model_path, map_location=self.device)
+            self.model.load_state_dict(state_dict, strict=True, assign=True)
+            self.model.to(self.device)
         self.model.eval()  # the reference forgets this; eval is the reproducible behaviour
         self.model.set_normalisation(mean, std)
         self.model.set_precision(precision)

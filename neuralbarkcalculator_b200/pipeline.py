@@ -1,0 +1,166 @@
+"""Folder pipeline behind ``predict.py``: raw scans on disk -> ``processed/`` PNGs, ``results/outputs`` PNGs and
+``results/final_stats.csv`` in ONE streaming pass (reference: predict.py:51-58 = Preprocessor.preprocess_images followed by
+NeuralBarkCalculator.predict, models.py:173-203 and 230-364).
+
+    reader threads : BMP pixel arrays -> pinned host buffers (file.readinto, no decode)
+    main thread    : batches of scans -> PredictEngine.submit_host / collect (K1, network, K3, K5 on the GPU; two batches
+                     in flight so the PCIe link stays busy)
+    writer threads : PNG encode of the processed image and of the 0/127/255 dual image (zlib releases the GIL)
+
+The files are the reference's (same names, same pixels, same CSV); only the PNG compression level is a knob
+(``png_compress_level``, pixels are unaffected).  Works for the standard input -- uncompressed 24-bit 4096x4096 BMP;
+``supported()`` says whether a folder qualifies, otherwise predict.py takes the per-image path of models.py."""
+import csv
+import os
+import struct
+import time
+from concurrent.futures import ThreadPoolExecutor
+from os.path import join
+
+import numpy as np
+import torch
+from ._png import write_png
+from .dataset import make_dataset
+from .engine import PredictEngine
+
+RAW = 4096
+CSV_HEADER = ['Name', 'Type', 'Image Size', 'Output Bark %', 'Bark area (mm^2)', 'Output Node %', 'Node area (mm^2)']
+_DUAL_LUT = np.array([0, 127, 255] + [0] * 253, dtype=np.uint8)     # models.py:349-353
+
+
+def bmp_geometry(path):
+    """(data offset, bottom_up) of an uncompressed 24-bit RAW x RAW BMP, else None."""
+    try:
+        with open(path, 'rb') as f:
+            head = f.read(54)
+    except OSError:
+        return None
+    if len(head) < 54 or head[:2] != b'BM':
+        return None
+    off = struct.unpack_from('<I', head, 10)[0]
+    hdr_size, w, h, planes, bpp, comp = struct.unpack_from('<IiiHHI', head, 14)
+    if hdr_size < 40 or bpp != 24 or comp != 0 or planes != 1 or w != RAW or abs(h) != RAW:
+        return None
+    return off, h > 0
+
+
+def supported(items):
+    """True when every input is a 4096x4096 24-bit BMP with one row orientation (what the scanner produces)."""
+    geo = [bmp_geometry(path) if path.lower().endswith('.bmp') else None for path, _, _, _ in items]
+    return len(geo) > 0 and all(g is not None for g in geo) and len({g[1] for g in geo}) == 1
+
+
+class FolderPipeline:
+    def __init__(self, calculator, batch=16, io_threads=None, png_compress_level=1):
+        self.calc = calculator
+        self.batch = batch
+        self.io_threads = io_threads or max(4, min(32, (os.cpu_count() or 8)))
+        self.png_level = png_compress_level
+        self.engine = PredictEngine(calculator.model, calculator.device, raw_size=RAW)
+
+    def _read_into(self, path, off, buf):
+        with open(path, 'rb', buffering=0) as f:
+            f.seek(off)
+            view = memoryview(buf.numpy())
+            got = 0
+            while got < len(view):
+                n = f.readinto(view[got:])
+                if not n:
+                    raise IOError('short read: ' + path)
+                got += n
+
+    def run(self, root_path, excludes_nodes, only_preprocess=False):
+        t_start = time.perf_counter()
+        timing = {'read_s': 0.0, 'save_s': 0.0}      # summed over the IO threads
+        items = make_dataset(root_path)
+        if len(items) == 0:
+            raise RuntimeError("Found 0 files in subfolders of: " + root_path)
+        geo = [bmp_geometry(p) for p, _, _, _ in items]
+        bottom_up = geo[0][1]
+        B = self.batch
+        nbytes = RAW * RAW * 3
+        # Pinned staging buffers: 3 batches' worth (2 in flight + 1 being read).  The MAIN thread hands them out as tokens
+        # in item order -- a reader can therefore never hold a buffer that an earlier item is still waiting for (a free-for-
+        # all pool deadlocks: later items overtake a parked reader and exhaust it) -- while the page-locking itself (about
+        # 1 s per GB) is done by the reader threads on a token's first use, overlapping the reads and the GPU work.
+        n_tokens = min(3 * B, len(items))
+        tokens = list(range(n_tokens))           # free tokens (main thread only)
+        pinned = [None] * n_tokens
+        mask_sets = [[torch.empty((RAW // 4) * (RAW // 4), dtype=torch.uint8).pin_memory() for _ in range(min(B, len(items)))]
+                     for _ in range(2)]
+        rows_csv = [None] * len(items)
+        out_proc = join(root_path, 'processed', 'samples')
+        out_dual = join(root_path, 'results', 'outputs')
+        Wo = RAW // 4
+        timing['setup_s'] = time.perf_counter() - t_start
+
+        def load(i, tok):
+            if pinned[tok] is None:
+                pinned[tok] = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+            t0 = time.perf_counter()
+            self._read_into(items[i][0], geo[i][0], pinned[tok])
+            timing['read_s'] += time.perf_counter() - t0
+            return tok
+
+        def save(i, proc, mask, counts):
+            t0 = time.perf_counter()
+            _, _, fname, wood = items[i]
+            fname = fname.replace('.bmp', '.png')           # models.py:185
+            write_png(join(out_proc, wood, fname), proc, self.png_level)
+            if mask is not None:
+                write_png(join(out_dual, wood, fname), _DUAL_LUT[mask], self.png_level)
+                rows_csv[i] = [fname, wood] + self.calc._stats_strings(counts, mask.size)
+            timing['save_s'] += time.perf_counter() - t0
+
+        readers, writers = ThreadPoolExecutor(self.io_threads), ThreadPoolExecutor(self.io_threads)
+        loads, fed = [None] * len(items), [0]
+
+        def feed():
+            while fed[0] < len(items) and tokens:
+                loads[fed[0]] = readers.submit(load, fed[0], tokens.pop(0))
+                fed[0] += 1
+
+        try:
+            pending, saves = [], []
+
+            def finish(entry):
+                ticket, idx, toks = entry
+                rows, counts, masks = self.engine.collect(ticket)
+                proc_host = ticket.slot.proc_host
+                for k, i in enumerate(idx):
+                    h = rows[k]
+                    proc = proc_host[k, :h].numpy().copy()
+                    mask = None if only_preprocess else masks[k][:h * Wo].numpy().reshape(h, Wo).copy()
+                    saves.append(writers.submit(save, i, proc, mask, None if only_preprocess else counts[k].tolist()))
+                tokens.extend(toks)      # the H2D copies of this batch are done: its staging buffers are free again
+                feed()
+
+            feed()
+            for a in range(0, len(items), B):
+                idx = list(range(a, min(a + B, len(items))))
+                toks = [loads[i].result() for i in idx]
+                ticket = self.engine.submit_host([pinned[t] for t in toks], None if only_preprocess else mask_sets[(a // B) & 1][:len(idx)],
+                                                 bgr=True, bottom_up=bottom_up, exclude_nodes=excludes_nodes, want_processed=True,
+                                                 only_preprocess=only_preprocess)
+                pending.append((ticket, idx, toks))
+                if len(pending) == 2:
+                    finish(pending.pop(0))
+            while pending:
+                finish(pending.pop(0))
+            for s in saves:
+                s.result()
+        finally:
+            for f in loads:
+                if f is not None:
+                    f.cancel()
+            readers.shutdown(wait=True)
+            writers.shutdown(wait=True)
+        timing['total_s'] = time.perf_counter() - t_start
+        timing['images'] = len(items)
+        self.last_timing = timing
+        if only_preprocess:
+            return None
+        results_csv = [CSV_HEADER] + rows_csv
+        with open(join(root_path, 'results', 'final_stats.csv'), 'w') as f:   # as models.py:360-364 (tab-delimited)
+            csv.writer(f, delimiter='\t').writerows(results_csv)
+        return results_csv

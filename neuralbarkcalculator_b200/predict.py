@@ -23,12 +23,32 @@ def generate_folders(root_path, only_preprocess):
                 os.makedirs(os.path.join(root_path, top, level, wood), exist_ok=True)
 
 
-def main(args):
+def main(args, state_dict=None):
+    """predict.py:51-58.  Folders of standard scans (4096x4096 24-bit BMP) go through the streaming FolderPipeline --
+    preprocessing and prediction fused into one pass with batched GPU work and threaded file IO; anything else takes the
+    per-image path of models.py.  Both write the same files."""
+    from .dataset import make_dataset
+    from . import pipeline
+    t0 = __import__('time').perf_counter()
     generate_folders(args.root_path, args.only_preprocess)
+    if pipeline.supported(make_dataset(args.root_path)):
+        model = NeuralBarkCalculator(None if state_dict is not None else './best_model.pt', args.device, state_dict=state_dict,
+                                     load_weights=not args.only_preprocess)
+        if os.environ.get('NBC_TIMING'):
+            print('[nbc] folders + model construction: %.3f s' % (__import__('time').perf_counter() - t0))
+        pipe = pipeline.FolderPipeline(model)
+        out = pipe.run(args.root_path, args.exclude_nodes, args.only_preprocess)
+        if os.environ.get('NBC_TIMING'):
+            import time
+            print('[nbc] folder pipeline timing: %s' % pipe.last_timing)
+            t1 = time.perf_counter()
+            del pipe, model
+            print('[nbc] teardown: %.3f s' % (time.perf_counter() - t1))
+        return out
     processed = Preprocessor(device=args.device).preprocess_images(args.root_path)
     if not args.only_preprocess:
-        model = NeuralBarkCalculator('./best_model.pt', args.device)
-        model.predict(args.root_path, args.exclude_nodes, processed=processed)
+        model = NeuralBarkCalculator('./best_model.pt', args.device, state_dict=state_dict)
+        return model.predict(args.root_path, args.exclude_nodes, processed=processed)
 
 
 def parse_args(argv=None):

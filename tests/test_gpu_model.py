@@ -202,3 +202,44 @@ def test_predict_pipeline_matches_oracle(cuda_device, synthetic_sd, tmp_path):
     with open(os.path.join(root, 'results', 'final_stats.csv')) as f:
         got = list(csv.reader(f, delimiter='\t'))
     assert got[0] == opost.CSV_HEADER and len(got) == 4 and all(len(r) == 6 for r in got[1:])
+
+
+def test_folder_pipeline_matches_per_image_path(cuda_device, synthetic_sd, tmp_path):
+    """predict.main() through the streaming FolderPipeline (batched ragged GPU work, threaded IO, two batches in flight)
+    writes the same processed PNGs, dual PNGs and CSV as the per-image path of models.py -- pixel for pixel."""
+    import argparse
+    import neuralbarkcalculator_b200 as nbc
+    from neuralbarkcalculator_b200 import pipeline, predict as npredict
+    from PIL import Image
+    root, root_b = str(tmp_path / 'pipe'), str(tmp_path / 'single')
+    for r in (root, root_b):
+        synth.make_raw_folder(r, 5, size=4096, pool=3, seed0=70)
+    npredict.generate_folders(root_b, False)
+    processed = nbc.Preprocessor(device='cuda:0').preprocess_images(root_b)
+    calc = nbc.NeuralBarkCalculator(None, 'cuda:0', state_dict=synthetic_sd)
+    rows_b = calc.predict(root_b, True, processed=processed)
+    # the pipeline, with a batch of 2 so that 5 images take 3 batches (slot reuse, a ragged last batch)
+    npredict.generate_folders(root, False)
+    from neuralbarkcalculator_b200.dataset import make_dataset
+    assert pipeline.supported(make_dataset(root))
+    rows = pipeline.FolderPipeline(calc, batch=2, io_threads=4).run(root, True)
+    assert rows == rows_b
+    for sub in (('processed', 'samples'), ('results', 'outputs')):
+        for wood in synth.WOOD_TYPES:
+            d = os.path.join(root, *sub, wood)
+            names = sorted(os.listdir(d))
+            assert names == sorted(os.listdir(os.path.join(root_b, *sub, wood))) and len(names) > 0
+            for fn in names:
+                a = np.asarray(Image.open(os.path.join(d, fn)))
+                b = np.asarray(Image.open(os.path.join(root_b, *sub, wood, fn)))
+                assert np.array_equal(a, b), '/'.join(sub) + '/' + wood + '/' + fn
+    with open(os.path.join(root, 'results', 'final_stats.csv')) as f, open(os.path.join(root_b, 'results', 'final_stats.csv')) as fb:
+        assert f.read() == fb.read()
+    # the CLI entry: --only_preprocess writes processed/ only and never needs the checkpoint
+    root_c = str(tmp_path / 'cli')
+    synth.make_raw_folder(root_c, 2, size=4096, pool=1, seed0=70)
+    npredict.main(argparse.Namespace(root_path=root_c, device='cuda:0', exclude_nodes=False, only_preprocess=True))
+    assert not os.path.exists(os.path.join(root_c, 'results'))
+    got = np.asarray(Image.open(os.path.join(root_c, 'processed', 'samples', synth.WOOD_TYPES[0], 'img_0000.png')))
+    ref = np.asarray(Image.open(os.path.join(root, 'processed', 'samples', synth.WOOD_TYPES[0], 'img_0000.png')))
+    assert np.array_equal(got, ref)

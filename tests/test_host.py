@@ -122,3 +122,22 @@ def test_stats_strings_match_reference_arithmetic(golden_dir):
     calc = nbc.NeuralBarkCalculator.__new__(nbc.NeuralBarkCalculator)
     calc.mm_per_pix = nbc.NeuralBarkCalculator.DEFAULT_MM_PER_PIXEL
     assert calc._stats_strings(counts.tolist(), mask.size) == list(g['strings'])
+
+
+def test_png_writer_roundtrip(tmp_path):
+    """The pipeline's own PNG encoder (RGB with Sub filter, grey masks, stored / fast / default deflate) decodes to the
+    same pixels with PIL."""
+    import io
+    from PIL import Image
+    from neuralbarkcalculator_b200 import _png
+    from oracle import synth
+    img = synth.texture_u8(37, 53, 1)
+    mask = (synth.class_mask(37, 53, 2) * 127).astype(np.uint8)
+    for level in (0, 1, 6):
+        assert np.array_equal(np.asarray(Image.open(io.BytesIO(_png.encode_png(img, level)))), img)
+        assert np.array_equal(np.asarray(Image.open(io.BytesIO(_png.encode_png(mask, level)))), mask)
+    assert np.array_equal(np.asarray(Image.open(io.BytesIO(_png.encode_png(img[:, :1], 1)))), img[:, :1])
+    _png.write_png(str(tmp_path / 'a.png'), img)
+    assert np.array_equal(np.asarray(Image.open(str(tmp_path / 'a.png'))), img)
+    with pytest.raises(ValueError):
+        _png.encode_png(img.astype(np.float32))

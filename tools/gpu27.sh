@@ -1,0 +1,8 @@
+set -x
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_gpu_model.py -q -m gpu --no-header -p no:cacheprovider -k "pipeline or engine" > gpurun_out/t_pipe.log 2>&1; echo "pytest exit $?"
+grep -v "Warning\|warn" gpurun_out/t_pipe.log | tail -n 5
+NBC_TIMING=1 timeout 900 python bench.py --workload cli --steps 2 --warmup 1 > gpurun_out/bench_cli.json 2> gpurun_out/bench_cli.err; echo "bench cli exit $?"
+tail -n 3 gpurun_out/bench_cli.err; grep -v "^{" gpurun_out/bench_cli.json; grep "^{" gpurun_out/bench_cli.json | cut -c1-200
+NBC_TIMING=1 timeout 900 python bench.py --workload cli --steps 1 --warmup 1 --batch 256 > gpurun_out/bench_cli256.json 2> gpurun_out/bench_cli256.err; echo "bench cli exit $?"
+grep -v "^{" gpurun_out/bench_cli256.json; grep "^{" gpurun_out/bench_cli256.json | cut -c1-200
