@@ -201,6 +201,9 @@ def main():
     dev = torch.device('cuda', local_rank)
     import neuralbarkcalculator_b200 as nbc
     from neuralbarkcalculator_b200 import _lib, engine
+    from neuralbarkcalculator_b200 import distributed as ndist
+    # one process per GPU: keep this rank's pinned staging buffers on the NUMA node of its GPU (see bind_to_gpu_numa)
+    numa = ndist.bind_to_gpu_numa(local_rank) if world > 1 else {'numa_node': ndist.gpu_numa_node(local_rank), 'bound': False}
 
     calc = nbc.NeuralBarkCalculator(None, str(dev), state_dict=sd)
     eng = engine.PredictEngine(calc.model, dev)
@@ -434,6 +437,7 @@ def main():
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
                 'config': {'workload': workload, 'images_per_step_per_gpu': n_img, 'parallelism': 'dp%d (images sharded, no collective)' % world,
+                           'numa': numa,
                            'l2': 'inputs (%.1f GB per rank) larger than L2; no flush needed' % (n_img * RAW * RAW * 3 / 1e9)},
                 'clocks': clocks, 'gpu_launches': launches, 'e2e': e2e, 'roofline': roof, 'cpu_baseline': cpu_base}
         print(json.dumps(line))

@@ -45,3 +45,46 @@ def merge_rows(local_rows, start, n_items):
     if any(r is None for r in merged):
         raise RuntimeError('merge_rows: shards do not cover the dataset')
     return merged
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(','):
+        if not part:
+            continue
+        lo, _, hi = part.partition('-')
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_node(device_index):
+    """NUMA node of a CUDA device from sysfs (None when it cannot be determined: no sysfs, single-node host, old torch)."""
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        dom, bus, dev = int(p.pci_domain_id), int(p.pci_bus_id), int(p.pci_device_id)
+        with open('/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node' % (dom, bus, dev)) as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPU cores of the NUMA node its GPU hangs off, BEFORE it allocates pinned host memory:
+    first-touch then places the staging buffers on that node and the 50 MB-per-scan host->device copies do not cross the
+    socket interconnect.  One process per GPU (torchrun) leaves placement to chance otherwise; with 8 ranks streaming
+    raw scans the inter-socket link, not PCIe, becomes the end-to-end bound.  Returns a small report dict."""
+    node = gpu_numa_node(device_index)
+    info = {'numa_node': node, 'bound': False}
+    if node is None:
+        return info
+    try:
+        with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, cpus)
+        info.update(bound=True, cpus=len(cpus))
+    except Exception as e:       # containers without sysfs / affinity rights: keep running unbound
+        info['error'] = str(e)
+    return info

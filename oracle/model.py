@@ -52,7 +52,7 @@ def fcn_resnet50(dropout=0.1):
     return SimpleSegmentationModel(backbone, FCNHead(2048, 3, dropout))
 
 
-def synthetic_state_dict(seed=0, logit_std=1.5, class_bias=(1.6, 0.2, -2.2), head=None):
+def synthetic_state_dict(seed=0, logit_std=1.5, class_bias=(1.6, 0.2, -2.2), head=None, branch_gain=0.5, calibration='whiten'):
     """Seeded random-init weights with *randomised BatchNorm* (SURVEY.md 8d config 0).
 
     Default torchvision init leaves BN at gamma=1, beta=0, mean=0, var=1, so a wrong BN fold would still pass and
@@ -76,11 +76,36 @@ def synthetic_state_dict(seed=0, logit_std=1.5, class_bias=(1.6, 0.2, -2.2), hea
         elif ('bn' in k or 'downsample.1' in k or k.startswith('classifier.1')) and k.endswith('.bias'):
             v.copy_(torch.randn(v.shape, generator=g) * 0.1)
     # The last BN of each bottleneck feeds the residual sum; keep the stream from exploding over 16 blocks.
+    # branch_gain: 0.5 (default) is a deliberately HARSH test network -- every block still changes the stream by ~50 %, so
+    # rounding noise is re-amplified 16 times; trained ResNets (and torchvision's zero_init_residual) sit near 0.1.
     for k in sd:
         if k.endswith('bn3.weight'):
-            sd[k].mul_(0.5)
-    if head is None:
+            sd[k].mul_(branch_gain)
+    if head is None and calibration == 'features':
+        # Classifier = three random directions on the STANDARDISED 512 head features, each class rescaled (diagonally) to
+        # logit_std / class_bias.  Unlike 'whiten' below -- which multiplies the raw logits by cov^(-1/2) and so blows the
+        # low-variance directions of three strongly correlated outputs, and any rounding noise in them, up by orders of
+        # magnitude -- this head has the noise gain of an ordinary trained linear layer.
         from . import synth
+        model.load_state_dict(sd)
+        model.eval()
+        with torch.no_grad():
+            feats = model.backbone(normalise_u8(synth.texture_u8(256, 256, seed=1234 + seed)))['out']
+            for layer in list(model.classifier.children())[:4]:      # conv3x3, BN, ReLU, Dropout (identity in eval)
+                feats = layer(feats)
+        F_ = feats.permute(0, 2, 3, 1).reshape(-1, feats.shape[1]).double()
+        mu_f, sd_f = F_.mean(0), F_.std(0)
+        alive = sd_f > 0.1 * sd_f.median()          # (nearly) constant channels carry no signal: weight 0, not 1/eps
+        R = torch.randn(3, feats.shape[1], generator=g).double()
+        Wd = torch.where(alive, R / sd_f.clamp_min(1e-12), torch.zeros_like(R))
+        L = (F_ - mu_f) @ Wd.T
+        scale = logit_std / L.std(0)
+        Wd = Wd * scale[:, None]
+        sd['classifier.4.weight'].copy_(Wd.float().view(3, -1, 1, 1))
+        sd['classifier.4.bias'].copy_(torch.tensor(class_bias) - (Wd @ mu_f).float())
+    elif head is None:
+        from . import synth
+        model.load_state_dict(sd)
         model.eval()
         with torch.no_grad():
             low = model.features(normalise_u8(synth.texture_u8(256, 256, seed=1234 + seed)))
