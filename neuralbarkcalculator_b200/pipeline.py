@@ -26,6 +26,24 @@ from .engine import PredictEngine
 RAW = 4096
 CSV_HEADER = ['Name', 'Type', 'Image Size', 'Output Bark %', 'Bark area (mm^2)', 'Output Node %', 'Node area (mm^2)']
 _DUAL_LUT = np.array([0, 127, 255] + [0] * 253, dtype=np.uint8)     # models.py:349-353
+# matplotlib's viridis at 0, 0.5, 1 -- the colours of classes 0 / 1 / 2 in the reference figure (imshow(vmax=2), models.py:300)
+_VIRIDIS3 = np.array([[68, 1, 84], [33, 145, 140], [253, 231, 37]] + [[0, 0, 0]] * 253, dtype=np.uint8)
+
+
+def combined_image(proc, mask, title):
+    """Stand-in for the reference's two-panel matplotlib figure (models.py:280-347; matplotlib is not a dependency here):
+    the processed image and the class mask in the figure's colours side by side at half resolution, the figure's
+    suptitle (class percentages) drawn in a strip above.  Same information, not the same rendering."""
+    from PIL import Image, ImageDraw
+    left = proc[::2, ::2]
+    right = _VIRIDIS3[mask[::2, ::2]]
+    h, w = left.shape[:2]
+    canvas = np.full((h + 16, 2 * w + 8, 3), 255, dtype=np.uint8)
+    canvas[16:, :w] = left
+    canvas[16:, w + 8:] = right
+    im = Image.fromarray(canvas)
+    ImageDraw.Draw(im).text((4, 2), title, fill=(0, 0, 0))
+    return np.asarray(im)
 
 
 def bmp_geometry(path):
@@ -54,6 +72,8 @@ class FolderPipeline:
     def __init__(self, calculator, batch=16, io_threads=None, png_compress_level=None):
         if png_compress_level is None:      # 0 = stored (fastest, 1.9 MB per processed image), 1 = fast deflate (default)
             png_compress_level = int(os.environ.get('NBC_PNG_LEVEL', '1'))
+        # results/combined_images/<wood>/<name>.png (the reference always writes its figure); NBC_COMBINED=0 skips it
+        self.combined = os.environ.get('NBC_COMBINED', '1') != '0'
         self.calc = calculator
         self.batch = batch
         self.io_threads = io_threads or max(4, min(32, (os.cpu_count() or 8)))
@@ -71,12 +91,19 @@ class FolderPipeline:
                     raise IOError('short read: ' + path)
                 got += n
 
-    def run(self, root_path, excludes_nodes, only_preprocess=False):
+    def run(self, root_path, excludes_nodes, only_preprocess=False, shard=None):
+        """shard=(start, end): process only that slice of the dataset order and return its CSV rows WITHOUT writing
+        final_stats.csv (data-parallel runs: one process per GPU, rank 0 merges the rows -- distributed.merge_rows)."""
         t_start = time.perf_counter()
         timing = {'read_s': 0.0, 'save_s': 0.0}      # summed over the IO threads
         items = make_dataset(root_path)
         if len(items) == 0:
             raise RuntimeError("Found 0 files in subfolders of: " + root_path)
+        if shard is not None:
+            items = items[shard[0]:shard[1]]
+            if len(items) == 0:
+                self.last_timing = {'images': 0}
+                return []
         geo = [bmp_geometry(p) for p, _, _, _ in items]
         bottom_up = geo[0][1]
         B = self.batch
@@ -93,6 +120,7 @@ class FolderPipeline:
         rows_csv = [None] * len(items)
         out_proc = join(root_path, 'processed', 'samples')
         out_dual = join(root_path, 'results', 'outputs')
+        out_comb = join(root_path, 'results', 'combined_images')
         Wo = RAW // 4
         timing['setup_s'] = time.perf_counter() - t_start
 
@@ -112,6 +140,10 @@ class FolderPipeline:
             if mask is not None:
                 write_png(join(out_dual, wood, fname), _DUAL_LUT[mask], self.png_level)
                 rows_csv[i] = [fname, wood] + self.calc._stats_strings(counts, mask.size)
+                if self.combined:
+                    st = rows_csv[i]
+                    title = 'Bark : %.3f;  Node : %.3f   (%s)' % (float(st[2]), float(st[4]), fname)    # cf. models.py:334-343
+                    write_png(join(out_comb, wood, fname), combined_image(proc, mask, title), self.png_level)
             timing['save_s'] += time.perf_counter() - t0
 
         readers, writers = ThreadPoolExecutor(self.io_threads), ThreadPoolExecutor(self.io_threads)
@@ -162,6 +194,8 @@ class FolderPipeline:
         self.last_timing = timing
         if only_preprocess:
             return None
+        if shard is not None:
+            return rows_csv
         results_csv = [CSV_HEADER] + rows_csv
         with open(join(root_path, 'results', 'final_stats.csv'), 'w') as f:   # as models.py:360-364 (tab-delimited)
             csv.writer(f, delimiter='\t').writerows(results_csv)

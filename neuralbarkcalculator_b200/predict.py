@@ -26,28 +26,52 @@ def generate_folders(root_path, only_preprocess):
 def main(args, state_dict=None):
     """predict.py:51-58.  Folders of standard scans (4096x4096 24-bit BMP) go through the streaming FolderPipeline --
     preprocessing and prediction fused into one pass with batched GPU work and threaded file IO; anything else takes the
-    per-image path of models.py.  Both write the same files."""
-    from .dataset import make_dataset
+    per-image path of models.py.  Both write the same files.
+
+    Under ``torchrun`` (one process per GPU) every rank takes a contiguous shard of the dataset order on cuda:LOCAL_RANK --
+    images are independent, there is no collective on the data path -- and rank 0 merges the CSV rows back into dataset
+    order, so the files are identical to a single-GPU run."""
+    import csv
+    import time
+    from . import distributed as ndist
     from . import pipeline
-    t0 = __import__('time').perf_counter()
-    generate_folders(args.root_path, args.only_preprocess)
-    if pipeline.supported(make_dataset(args.root_path)):
-        model = NeuralBarkCalculator(None if state_dict is not None else './best_model.pt', args.device, state_dict=state_dict,
+    from .dataset import make_dataset
+    rank, local_rank, world = ndist.env_world()
+    device = args.device
+    if world > 1:
+        device = 'cuda:%d' % local_rank
+        ndist.init_from_env('cuda')
+        ndist.bind_to_gpu_numa(local_rank)
+    t0 = time.perf_counter()
+    if rank == 0:
+        generate_folders(args.root_path, args.only_preprocess)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    items = make_dataset(args.root_path)
+    if pipeline.supported(items):
+        model = NeuralBarkCalculator(None if state_dict is not None else './best_model.pt', device, state_dict=state_dict,
                                      load_weights=not args.only_preprocess)
         if os.environ.get('NBC_TIMING'):
-            print('[nbc] folders + model construction: %.3f s' % (__import__('time').perf_counter() - t0))
+            print('[nbc] folders + model construction: %.3f s' % (time.perf_counter() - t0))
         pipe = pipeline.FolderPipeline(model)
-        out = pipe.run(args.root_path, args.exclude_nodes, args.only_preprocess)
+        shard = ndist.shard_bounds(len(items), rank, world) if world > 1 else None
+        out = pipe.run(args.root_path, args.exclude_nodes, args.only_preprocess, shard=shard)
+        if world > 1 and not args.only_preprocess:
+            rows = ndist.merge_rows(out, shard[0], len(items))
+            out = None
+            if rank == 0:
+                out = [pipeline.CSV_HEADER] + rows
+                with open(os.path.join(args.root_path, 'results', 'final_stats.csv'), 'w') as f:   # models.py:360-364
+                    csv.writer(f, delimiter='\t').writerows(out)
         if os.environ.get('NBC_TIMING'):
-            import time
             print('[nbc] folder pipeline timing: %s' % pipe.last_timing)
-            t1 = time.perf_counter()
-            del pipe, model
-            print('[nbc] teardown: %.3f s' % (time.perf_counter() - t1))
         return out
-    processed = Preprocessor(device=args.device).preprocess_images(args.root_path)
+    if world > 1:
+        raise RuntimeError('multi-GPU predict needs the standard input (4096x4096 24-bit BMP scans)')
+    processed = Preprocessor(device=device).preprocess_images(args.root_path)
     if not args.only_preprocess:
-        model = NeuralBarkCalculator('./best_model.pt', args.device, state_dict=state_dict)
+        model = NeuralBarkCalculator('./best_model.pt', device, state_dict=state_dict)
         return model.predict(args.root_path, args.exclude_nodes, processed=processed)
 
 

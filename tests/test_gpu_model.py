@@ -239,6 +239,11 @@ def test_folder_pipeline_matches_per_image_path(cuda_device, synthetic_sd, tmp_p
                 assert np.array_equal(a, b), '/'.join(sub) + '/' + wood + '/' + fn
     with open(os.path.join(root, 'results', 'final_stats.csv')) as f, open(os.path.join(root_b, 'results', 'final_stats.csv')) as fb:
         assert f.read() == fb.read()
+    # the stand-in for the matplotlib figure: one half-resolution two-panel PNG per image under results/combined_images
+    comb = os.path.join(root, 'results', 'combined_images', synth.WOOD_TYPES[0], 'img_0000.png')
+    ci = np.asarray(Image.open(comb))
+    pr = np.asarray(Image.open(os.path.join(root, 'processed', 'samples', synth.WOOD_TYPES[0], 'img_0000.png')))
+    assert ci.shape == ((pr.shape[0] + 1) // 2 + 16, 2 * 512 + 8, 3) and np.array_equal(ci[16:, :512], pr[::2, ::2])
     # the CLI entry: --only_preprocess writes processed/ only and never needs the checkpoint
     root_c = str(tmp_path / 'cli')
     synth.make_raw_folder(root_c, 2, size=4096, pool=1, seed0=70)
