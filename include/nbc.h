@@ -154,6 +154,20 @@ int nbc_argmax3_u8(const float* logits, int N, int H, int W, uint8_t* out, void*
 int nbc_confusion_matrix(const uint8_t* pred, const void* target, int target_is_i64, int64_t n_pixels, uint64_t* cm9,
                          void* stream);
 
+/* ---- N4: training-time augmentation of a batch  (__main__.py:153-176 get_loader_for_crop_batch; dataset.py:171-193) --
+ * images u8 [M,Hs,Ws,3] and their dual label images u8 [M,Hs,Ws] (0/127/255) resident on the device; for each of the B
+ * output samples the caller draws the parameters: source index, crop offset (x0, y0) in the pad_resize'd (reflect-padded
+ * to target_w x target_h; the differences must be even) image, flips, colour-jitter factors and their order.  One fused
+ * gather: out_images u8 [B,crop,crop,3] (PIL ImageEnhance arithmetic, bit-exact), out_classes u8 [B,crop,crop] =
+ * round(ToTensor(jittered dual) * 2).  duals / out_classes may both be NULL. */
+typedef struct {
+  int32_t src, x0, y0, hflip, vflip, order; /* order: 0 = brightness then saturation, 1 = saturation then brightness */
+  float brightness, saturation;             /* factors; <= 0 disables the op */
+} nbc_augment_params;
+int nbc_augment_batch(const uint8_t* images, const uint8_t* duals, int M, int Hs, int Ws, int target_h, int target_w,
+                      int crop, const nbc_augment_params* params, int B, uint8_t* out_images, uint8_t* out_classes,
+                      void* stream);
+
 /* ---- the whole network  (models.py:27-43 SimpleSegmentationModel.forward, 127-139 fcn_resnet50) ------------------
  * tensors_host: host array of DEVICE pointers to the 326 f32 state_dict tensors in torchvision key order
  * (backbone.conv1.weight, backbone.bn1.{weight,bias,running_mean,running_var,num_batches_tracked}, ...).

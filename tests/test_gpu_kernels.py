@@ -456,3 +456,35 @@ def test_metrics_vs_oracle(cuda_device, golden_dir):
         ours = nutils.PixelWiseF1(watch)(big.to(cuda_device), lab.to(cuda_device))
         ref = olovasz.pixelwise_f1(big, lab, watch)
         assert np.allclose(ours, ref, rtol=0, atol=1e-12), (watch, ours, ref)
+
+
+# ------------------------------------------------------------------------------------------------- N4 augmentation
+def test_augment_batch_vs_oracle(cuda_device):
+    """The fused crop / flip / reflect-pad / colour-jitter gather == the reference's torchvision-on-PIL chain, bit for bit."""
+    from oracle import augment as oaug
+    from neuralbarkcalculator_b200 import augment as naug
+    synth = _synth()
+    rng = np.random.default_rng(5)
+    for (Hs, Ws, target, crop) in ((1024, 1024, (1024, 1024), 512), (1000, 1024, (1024, 1024), 384), (96, 80, (100, 84), 64)):
+        images = [synth.texture_u8(Hs, Ws, 40 + i) for i in range(3)]
+        duals = [(synth.class_mask(Hs, Ws, 50 + i).astype(np.float32) * 127.5).astype(np.uint8) for i in range(3)]
+        params = naug.draw_params(rng, 6, 3, crop, target)
+        params['brightness'][0], params['saturation'][1] = 0.0, 0.0          # disabled ops
+        params['brightness'][2], params['saturation'][2] = 1.0, 1.0          # factor exactly 1 still goes through PIL
+        plist = [{k: (float(p[k]) if k in ('brightness', 'saturation') else int(p[k])) for k in naug.PARAM_DTYPE.names} for p in params]
+        ref_i, ref_c = oaug.augment(images, duals, plist, crop, target)
+        out, cls = naug.augment_batch(torch.from_numpy(np.stack(images)).to(cuda_device), torch.from_numpy(np.stack(duals)).to(cuda_device),
+                                      params, crop, target)
+        assert np.array_equal(out.cpu().numpy(), ref_i), (Hs, Ws)
+        assert np.array_equal(cls.cpu().numpy(), ref_c), (Hs, Ws)
+    with pytest.raises(RuntimeError):        # an odd difference would need PIL's resize: rejected, never approximated
+        naug.augment_batch(torch.zeros(1, 1001, 1024, 3, dtype=torch.uint8, device=cuda_device), None, naug.draw_params(rng, 1, 1, 256), 256)
+    # end to end: an augmented batch feeds the native training step
+    from neuralbarkcalculator_b200.train import Trainer
+    from oracle import model as omodel
+    sd = omodel.synthetic_state_dict(seed=0, head=None)
+    images = torch.from_numpy(np.stack([synth.texture_u8(128, 128, 60 + i) for i in range(2)])).to(cuda_device)
+    duals = torch.from_numpy(np.stack([(synth.class_mask(128, 128, 70 + i).astype(np.float32) * 127.5).astype(np.uint8) for i in range(2)])).to(cuda_device)
+    x, t = naug.augment_batch(images, duals, naug.draw_params(rng, 2, 2, 64, (128, 128)), 64, (128, 128))
+    tr = Trainer(sd, 2, 64, 64, device='cuda:0', dropout=0.0)
+    assert np.isfinite(float(tr.step(x, t)))

@@ -193,3 +193,34 @@ def test_lovasz_oracle_properties():
     sk = f1_score(lab.reshape(-1), pred.reshape(-1), labels=[0, 1, 2], average=None, zero_division=0)
     sk[2] = np.delete(sk, 2).mean()
     assert np.allclose(olovasz.f1_from_confusion(cm), sk)
+
+
+# ------------------------------------------------------------------------------------------------- N4 augmentation
+def test_augment_oracle_and_pil_arithmetic():
+    """(1) The arithmetic csrc/augment.cu implements -- PIL's ImageEnhance blend (f32, truncation, clip outside [0,1]) and
+    integer luma -- restated in numpy equals torchvision's adjust_brightness / adjust_saturation on PIL images exactly;
+    (2) the oracle chain applies the explicit parameters in the reference's order."""
+    from PIL import Image
+    from torchvision.transforms import functional as TF
+    from oracle import augment as oaug
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (48, 40, 3), dtype=np.uint8)
+    i64 = img.astype(np.int64)
+    L = ((19595 * i64[..., 0] + 38470 * i64[..., 1] + 7471 * i64[..., 2] + 0x8000) >> 16).astype(np.int32)
+
+    def blend(a, v, f):
+        t = (a.astype(np.float32) + np.float32(f) * (v.astype(np.int32) - a.astype(np.int32)).astype(np.float32)).astype(np.float32)
+        if 0 <= f <= 1:
+            return t.astype(np.int32)
+        return np.where(t <= 0, 0, np.where(t >= 255, 255, t.astype(np.int32)))
+    for f in (0.9, 0.95, 1.0, 1.05, 1.1, 0.8123, 1.1999):
+        assert np.array_equal(np.asarray(TF.adjust_brightness(Image.fromarray(img), f)), blend(np.zeros_like(L)[..., None], img, f))
+        assert np.array_equal(np.asarray(TF.adjust_saturation(Image.fromarray(img), f)),
+                              np.stack([blend(L, img[..., c], f) for c in range(3)], -1))
+    dual = (rng.integers(0, 3, (48, 40)) * 127.5).astype(np.uint8)
+    p = dict(src=0, x0=3, y0=5, hflip=1, vflip=0, order=0, brightness=0.0, saturation=0.0)
+    oi, oc = oaug.augment([img], [dual], [p], crop=16, target_hw=(48, 40))
+    assert np.array_equal(oi[0], img[5:21, 3:19][:, ::-1]) and np.array_equal(oc[0], np.round(dual[5:21, 3:19][:, ::-1] / 255.0 * 2))
+    # reflect padding (even difference): 44 rows -> 48, two rows mirrored on each side without repeating the edge
+    oi, _ = oaug.augment([img[2:46]], [dual[2:46]], [dict(p, x0=0, y0=0, hflip=0)], crop=40, target_hw=(48, 40))
+    assert np.array_equal(oi[0][:3], img[2:46][[2, 1, 0]])
