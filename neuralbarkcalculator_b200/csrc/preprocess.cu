@@ -6,10 +6,13 @@
 //     S = sum_{p,q} w_p w_q * in[4i+p, 4j+q]   (exact int, = 256 * resized value)
 //     out = clamp((S + 128) >> 8, min(in), max(in))        -- skimage clips to the input range, then u8 rounding
 //     nondark(i,j) = sum_c clip(S_c) / (256*255) > 1e-3   <=>  min(in) >= 1  or  sum_c max(S_c, 0) >= 66
-// Pass 1 reads the raw image once (coalesced 16-byte loads, 48 B per thread per row), writes (S+128)>>8 as int16,
-// and reduces the input min / max and the per-row non-dark counts.  A one-block kernel turns the counts into the
-// [first, last) rows (keep a row iff > 85 % of its pixels are non-dark).  Pass 2 clamps and compacts the rows.
+// Pass 1 reads the raw image once (16-byte loads, 48 B per thread per row), writes (S+128)>>8 saturated to u8
+// (coalesced 16-byte stores through shared memory), and reduces the input min / max and the per-row non-dark counts.
+// A one-block kernel turns the counts into the [first, last) rows (keep a row iff > 85 % of its pixels are non-dark).
+// Pass 2 clamps to the input range and compacts the rows.
 // The BMP pixel array (bottom-up, BGR) is consumed directly: flags bit0 = BGR, bit1 = bottom-up.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace nbc {
@@ -22,82 +25,125 @@ struct PreHeader {
 
 __device__ __forceinline__ int byte_of(uint32_t v, int i) { return (v >> (8 * i)) & 0xFF; }
 
+// The 48 source bytes of 4 output pixels on each of the 4 source rows of output row ho (zero where the thread is idle)
+template <bool kAligned>
+__device__ __forceinline__ void pass1_load(const uint8_t* __restrict__ raw, int H, int64_t pitch, int flags, int ho, int wo0,
+                                           int npx, uint32_t (&words)[4][12]) {
+  const int nbytes = npx * 12;
+#pragma unroll
+  for (int pr = 0; pr < 4; ++pr) {
+    const int r = 4 * ho + pr;
+    const int64_t rr = (flags & 2) ? (int64_t)(H - 1 - r) : (int64_t)r;
+    const uint8_t* src = raw + rr * pitch + (int64_t)wo0 * 12;
+    if (kAligned && npx == 4) {
+      const uint4* s4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const uint4 v = __ldg(s4 + i);
+        words[pr][4 * i] = v.x, words[pr][4 * i + 1] = v.y, words[pr][4 * i + 2] = v.z, words[pr][4 * i + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int idx = 4 * i + b;
+          // replicate the first byte into the padding so it does not disturb min / max
+          const uint32_t byte = (idx < nbytes) ? src[idx] : src[0];
+          v |= byte << (8 * b);
+        }
+        words[pr][i] = v;
+      }
+    }
+  }
+}
+
+// One block = one output row (256 threads x 4 output pixels).  The results leave as u8 SATURATED to [0, 255] -- pass 2
+// clamps to the input range [lo, hi], a sub-interval, so clamp(clamp(v, 0, 255), lo, hi) == clamp(v, lo, hi) -- staged
+// through shared memory so that a warp's 384 output bytes go out as 24 coalesced 16-byte stores instead of 384 two-byte
+// ones (the partial-sector writes of the first version cost more than the 50 MB of reads).
 template <bool kAligned>
 __global__ void __launch_bounds__(256) resize4x_pass1(const uint8_t* __restrict__ raw, int H, int W, int64_t pitch,
-                                                      int flags, int16_t* __restrict__ r16, PreHeader* hdr,
+                                                      int flags, uint8_t* __restrict__ r8, PreHeader* hdr,
                                                       int* __restrict__ rowcount) {
+  __shared__ __align__(16) uint32_t s_out[8][96];   // per warp: 32 threads x 12 bytes
   const int Wo = W >> 2;
   const int groups = (Wo + 3) >> 2;  // 4 output pixels per thread
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const int ho = blockIdx.y;
   const bool active = g < groups;
+  const int wo0 = g << 2;
+  const int npx = active ? min(4, Wo - wo0) : 0;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t mn2 = 0xFFFFFFFFu, mx2 = 0u;   // min / max as two 16-bit fields
   int nondark = 0;
-  uint32_t vmin = 0xFFFFFFFFu, vmax = 0u;
+  uint32_t packed[3] = {0u, 0u, 0u};      // the thread's 12 output bytes (4 pixels x RGB)
   if (active) {
-    const int wo0 = g << 2;
-    const int npx = min(4, Wo - wo0);
-    const int nbytes = npx * 12;
-    int V[48];
+    uint32_t cur[4][12];
+    pass1_load<kAligned>(raw, H, pitch, flags, ho, wo0, npx, cur);
+    // Vertical pass on PACKED 16-bit fields: each word (4 bytes of one row) is widened to two words of two 16-bit
+    // fields (PRMT), so that min / max are one min.u16x2 / max.u16x2 each and the 4-tap column filter is plain 32-bit
+    // integer arithmetic on two columns at once:  V' = 9 (r1 + r2) + 1020 - (r0 + r3)  in [0, 5610] -- no carry
+    // between fields, never negative.  Horizontal pass: S = -V'[b] + 9 V'[b+3] + 9 V'[b+6] - V'[b+9] - 16 * 1020.
+    uint32_t Vp[24];   // field f (byte column f of the 48) lives in Vp[f >> 1], bits 16 * (f & 1)
 #pragma unroll
-    for (int i = 0; i < 48; ++i) V[i] = 0;
+    for (int i = 0; i < 12; ++i) {
+      uint32_t e[4][2];
 #pragma unroll
-    for (int pr = 0; pr < 4; ++pr) {
-      const int r = 4 * ho + pr;
-      const int64_t rr = (flags & 2) ? (int64_t)(H - 1 - r) : (int64_t)r;
-      const uint8_t* src = raw + rr * pitch + (int64_t)wo0 * 12;
-      uint32_t words[12];
-      if (kAligned && npx == 4) {
-        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+      for (int pr = 0; pr < 4; ++pr) {
+        e[pr][0] = __byte_perm(cur[pr][i], 0u, 0x4140);   // bytes 0, 1 -> fields
+        e[pr][1] = __byte_perm(cur[pr][i], 0u, 0x4342);   // bytes 2, 3 -> fields
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const uint4 v = __ldg(s4 + i);
-          words[4 * i] = v.x, words[4 * i + 1] = v.y, words[4 * i + 2] = v.z, words[4 * i + 3] = v.w;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 12; ++i) {
-          uint32_t v = 0;
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const int idx = 4 * i + b;
-            // replicate the first byte into the padding so it does not disturb min / max
-            const uint32_t byte = (idx < nbytes) ? src[idx] : src[0];
-            v |= byte << (8 * b);
-          }
-          words[i] = v;
+        for (int k = 0; k < 2; ++k) {
+          asm("min.u16x2 %0, %0, %1;" : "+r"(mn2) : "r"(e[pr][k]));
+          asm("max.u16x2 %0, %0, %1;" : "+r"(mx2) : "r"(e[pr][k]));
         }
       }
-      const int wgt = (pr == 0 || pr == 3) ? -1 : 9;
 #pragma unroll
-      for (int i = 0; i < 12; ++i) {
-        vmin = __vminu4(vmin, words[i]);
-        vmax = __vmaxu4(vmax, words[i]);
-#pragma unroll
-        for (int b = 0; b < 4; ++b) V[4 * i + b] += wgt * byte_of(words[i], b);
-      }
+      for (int k = 0; k < 2; ++k)
+        Vp[2 * i + k] = 9u * (e[1][k] + e[2][k]) + (0x03FC03FCu - (e[0][k] + e[3][k]));   // 0x03FC = 1020 in both fields
     }
-    // horizontal pass: output pixel px uses input pixels 4px..4px+3 (3 bytes each)
+    auto field = [&](int f) { return (int)((Vp[f >> 1] >> (16 * (f & 1))) & 0xFFFFu); };
 #pragma unroll
     for (int px = 0; px < 4; ++px) {
       if (px < npx) {
-        int S[3];
+        int Sp[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const int b = px * 12 + c;
-          S[c] = -V[b] + 9 * V[b + 3] + 9 * V[b + 6] - V[b + 9];
+          const int b = px * 12 + c;     // byte column of tap 0; taps are 3 columns apart
+          Sp[c] = -field(b) + 9 * field(b + 3) + 9 * field(b + 6) - field(b + 9) - 16 * 1020;
         }
-        const int s0 = (flags & 1) ? S[2] : S[0], s2 = (flags & 1) ? S[0] : S[2];  // BGR -> RGB
-        int16_t* o = r16 + ((int64_t)ho * Wo + wo0 + px) * 3;
-        o[0] = (int16_t)((s0 + 128) >> 8);
-        o[1] = (int16_t)((S[1] + 128) >> 8);
-        o[2] = (int16_t)((s2 + 128) >> 8);
-        nondark += (max(S[0], 0) + max(S[1], 0) + max(S[2], 0)) >= 66 ? 1 : 0;
+        nondark += (max(Sp[0], 0) + max(Sp[1], 0) + max(Sp[2], 0)) >= 66 ? 1 : 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int sc = (flags & 1) ? Sp[2 - c] : Sp[c];                  // BGR -> RGB
+          const uint32_t v = (uint32_t)min(max((sc + 128) >> 8, 0), 255);
+          const int byte = px * 3 + c;
+          packed[byte >> 2] |= v << (8 * (byte & 3));
+        }
       }
     }
   }
-  // reductions: bytes -> scalar min/max, then warp, then one atomic per warp
-  int mn = min(min(byte_of(vmin, 0), byte_of(vmin, 1)), min(byte_of(vmin, 2), byte_of(vmin, 3)));
-  int mx = max(max(byte_of(vmax, 0), byte_of(vmax, 1)), max(byte_of(vmax, 2), byte_of(vmax, 3)));
+  // output: the warp's 32 x 12 bytes are contiguous in the row; stage them and store 16 bytes per lane
+  s_out[wid][lane * 3] = packed[0], s_out[wid][lane * 3 + 1] = packed[1], s_out[wid][lane * 3 + 2] = packed[2];
+  __syncwarp();
+  {
+    const int wo_warp = (blockIdx.x * blockDim.x + wid * 32) << 2;        // first output pixel of this warp
+    const int valid_bytes = max(0, min(128, Wo - wo_warp)) * 3;           // bytes of the row this warp owns
+    uint8_t* dst = r8 + ((int64_t)ho * Wo + wo_warp) * 3;
+    const bool vec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    int tail = 0;                                                         // first byte the byte loop has to store
+    if (vec) {
+      if (lane * 16 + 16 <= valid_bytes) reinterpret_cast<uint4*>(dst)[lane] = reinterpret_cast<const uint4*>(s_out[wid])[lane];
+      tail = valid_bytes & ~15;
+    }
+    const uint8_t* sb = reinterpret_cast<const uint8_t*>(s_out[wid]);
+    for (int i = tail + lane; i < valid_bytes; i += 32) dst[i] = sb[i];      // unaligned rows / the ragged end of a row
+  }
+  // reductions: warp, then one (min, max, count) per block; the two range atomics all land on the same address, so
+  // they are skipped when they cannot change it (the values only grow, a stale read just means one redundant atomic)
+  int mn = (int)min(mn2 & 0xFFFFu, mn2 >> 16), mx = (int)max(mx2 & 0xFFFFu, mx2 >> 16);
   if (!active) mn = 255, mx = 0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -105,11 +151,8 @@ __global__ void __launch_bounds__(256) resize4x_pass1(const uint8_t* __restrict_
     mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     nondark += __shfl_xor_sync(0xffffffffu, nondark, o);
   }
-  // one (min, max, count) per block; the two range atomics all land on the same address, so they are skipped when
-  // they cannot change it (the values only grow, a stale read just means one redundant atomic)
   __shared__ int s_mn[8], s_mx[8], s_nd[8];
-  const int wid = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0) s_mn[wid] = mn, s_mx[wid] = mx, s_nd[wid] = nondark;
+  if (lane == 0) s_mn[wid] = mn, s_mx[wid] = mx, s_nd[wid] = nondark;
   __syncthreads();
   if (threadIdx.x == 0) {
     const int nw = (blockDim.x + 31) >> 5;
@@ -162,28 +205,24 @@ __global__ void __launch_bounds__(1024) trim_rows_kernel(const int* __restrict__
   }
 }
 
-__global__ void __launch_bounds__(256) resize4x_pass2(const int16_t* __restrict__ r16, const PreHeader* hdr, int Wo,
+__global__ void __launch_bounds__(256) resize4x_pass2(const uint8_t* __restrict__ r8, const PreHeader* hdr, int Wo,
                                                       const int32_t* __restrict__ first_last,
                                                       uint8_t* __restrict__ out) {
   const int first = first_last[0], last = first_last[1];
-  const int lo = 255 - hdr->inv_min, hi = hdr->max;
+  const uint32_t lo = (uint32_t)(255 - hdr->inv_min), hi = (uint32_t)hdr->max;
+  const uint32_t lo4 = lo * 0x01010101u, hi4 = hi * 0x01010101u;
   const int64_t total = (int64_t)(last - first) * Wo * 3;
-  const int16_t* src = r16 + (int64_t)first * Wo * 3;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 8;
-  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < total; i += stride) {
-    if (i + 8 <= total && ((reinterpret_cast<uintptr_t>(src + i) & 15) == 0) &&
-        ((reinterpret_cast<uintptr_t>(out + i) & 7) == 0)) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + i));
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-      uint32_t o[2] = {0, 0};
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int s = (int)(int16_t)((w[k >> 1] >> ((k & 1) * 16)) & 0xFFFF);
-        o[k >> 2] |= (uint32_t)min(max(s, lo), hi) << ((k & 3) * 8);
-      }
-      *reinterpret_cast<uint2*>(out + i) = make_uint2(o[0], o[1]);
+  const uint8_t* src = r8 + (int64_t)first * Wo * 3;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 16;
+  const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; i < total; i += stride) {
+    if (vec && i + 16 <= total) {
+      uint4 v = __ldg(reinterpret_cast<const uint4*>(src + i));
+      v.x = __vminu4(__vmaxu4(v.x, lo4), hi4), v.y = __vminu4(__vmaxu4(v.y, lo4), hi4);
+      v.z = __vminu4(__vmaxu4(v.z, lo4), hi4), v.w = __vminu4(__vmaxu4(v.w, lo4), hi4);
+      *reinterpret_cast<uint4*>(out + i) = v;
     } else {
-      for (int64_t j = i; j < min(i + 8, total); ++j) out[j] = (uint8_t)min(max((int)src[j], lo), hi);
+      for (int64_t j = i; j < min(i + 16, total); ++j) out[j] = (uint8_t)min(max((uint32_t)src[j], lo), hi);
     }
   }
 }
@@ -222,21 +261,21 @@ extern "C" int nbc_preprocess_4x_u8(const uint8_t* raw, int H, int W, int64_t pi
   char* ws = reinterpret_cast<char*>(workspace);
   PreHeader* hdr = reinterpret_cast<PreHeader*>(ws);
   int* rowcount = reinterpret_cast<int*>(ws + sizeof(PreHeader));
-  int16_t* r16 = reinterpret_cast<int16_t*>(ws + pre_header_bytes(H));
+  uint8_t* r8 = reinterpret_cast<uint8_t*>(ws + pre_header_bytes(H));     // saturated u8 intermediate, Ho x Wo x 3
   NBC_CUDA(cudaMemsetAsync(ws, 0, sizeof(PreHeader) + (size_t)Ho * sizeof(int), stream));
   const int groups = (Wo + 3) / 4;
   dim3 grid(ceil_div(groups, 256), Ho);
   const bool aligned = (reinterpret_cast<uintptr_t>(raw) % 16 == 0) && (pitch % 16 == 0);
   if (aligned)
-    resize4x_pass1<true><<<grid, 256, 0, stream>>>(raw, H, W, pitch, flags, r16, hdr, rowcount);
+    resize4x_pass1<true><<<grid, 256, 0, stream>>>(raw, H, W, pitch, flags, r8, hdr, rowcount);
   else
-    resize4x_pass1<false><<<grid, 256, 0, stream>>>(raw, H, W, pitch, flags, r16, hdr, rowcount);
+    resize4x_pass1<false><<<grid, 256, 0, stream>>>(raw, H, W, pitch, flags, r8, hdr, rowcount);
   NBC_CHECK_LAUNCH();
   trim_rows_kernel<<<1, 1024, 0, stream>>>(rowcount, hdr, Ho, Wo, Ho == Wo ? 1 : 0, first_last);
   NBC_CHECK_LAUNCH();
-  const int64_t total8 = ceil_div64((int64_t)Ho * Wo * 3, 8);
-  const int blocks = (int)(total8 < 256 ? 1 : (ceil_div64(total8, 256) < 4 * 148 ? ceil_div64(total8, 256) : 4 * 148));
-  resize4x_pass2<<<blocks, 256, 0, stream>>>(r16, hdr, Wo, first_last, out);
+  const int64_t total16 = ceil_div64((int64_t)Ho * Wo * 3, 16);
+  const int blocks = (int)(total16 < 256 ? 1 : (ceil_div64(total16, 256) < 4 * 148 ? ceil_div64(total16, 256) : 4 * 148));
+  resize4x_pass2<<<blocks, 256, 0, stream>>>(r8, hdr, Wo, first_last, out);
   NBC_CHECK_LAUNCH();
   return 0;
 }
