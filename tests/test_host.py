@@ -141,3 +141,31 @@ def test_png_writer_roundtrip(tmp_path):
     assert np.array_equal(np.asarray(Image.open(str(tmp_path / 'a.png'))), img)
     with pytest.raises(ValueError):
         _png.encode_png(img.astype(np.float32))
+
+
+def test_pipeline_and_numa_host_helpers(tmp_path):
+    """Host-side pieces of the folder pipeline and of the one-process-per-GPU plumbing (no GPU needed)."""
+    import struct
+    from neuralbarkcalculator_b200 import augment, distributed as ndist, pipeline
+    from oracle import synth
+    # BMP geometry probe: only uncompressed 24-bit 4096x4096 files qualify for the streaming pipeline
+    small = str(tmp_path / 's.bmp')
+    synth.write_bmp(small, synth.texture_u8(8, 8, 0))
+    assert pipeline.bmp_geometry(small) is None and pipeline.bmp_geometry(str(tmp_path / 'missing.bmp')) is None
+    big = str(tmp_path / 'b.bmp')
+    with open(small, 'rb') as f:
+        head = bytearray(f.read(54))
+    struct.pack_into('<ii', head, 18, 4096, 4096)          # same header, claimed size 4096 x 4096, bottom-up
+    with open(big, 'wb') as f:
+        f.write(bytes(head))
+    assert pipeline.bmp_geometry(big) == (54, True)
+    assert not pipeline.supported([(small, None, 's.png', 'sapin')]) and not pipeline.supported([])
+    title_img = pipeline.combined_image(synth.texture_u8(20, 32, 1), synth.class_mask(20, 32, 2), 'Bark : 1.000')
+    assert title_img.shape == (10 + 16, 2 * 16 + 8, 3)
+    # NUMA helpers degrade gracefully without sysfs / without a GPU
+    assert ndist._parse_cpulist('0-3,8,10-11\n') == {0, 1, 2, 3, 8, 10, 11}
+    assert ndist.bind_to_gpu_numa(0)['bound'] in (True, False)
+    # augmentation draws respect the transforms' ranges
+    p = augment.draw_params(np.random.default_rng(0), 64, 5, 512)
+    assert p['x0'].max() <= 512 and p['y0'].min() >= 0 and set(np.unique(p['order'])) <= {0, 1} and p['src'].max() < 5
+    assert 0.9 <= p['brightness'].min() and p['brightness'].max() <= 1.1 and 0.8 <= p['saturation'].min() and p['saturation'].max() <= 1.2
