@@ -78,6 +78,13 @@ typedef struct {
 int nbc_conv_bf16(const nbc_conv_desc* desc, const void* x, const void* w_packed, const float* bias,
                   const void* residual, void* y, void* stream);
 
+/* Two sources, one accumulator: y = act(conv(x; w[:, :K1]) + conv1x1(x2; w[:, K1:]) + bias) -- a bottleneck's conv3 with
+ * its downsample branch (torchvision Bottleneck.forward: out = conv3(...) ; identity = downsample(x); out += identity)
+ * as ONE launch.  desc: the main convolution (stride 1); desc2: a 1x1 convolution (stride 1 or 2, pad 0) of x2 with the
+ * same output geometry; w_cat: [Cout][K1 + Cin2] (per output channel: main weights then the second source's). tcgen05 only. */
+int nbc_conv_dual_bf16(const nbc_conv_desc* desc, const void* x, const nbc_conv_desc* desc2, const void* x2,
+                       const void* w_cat, const float* bias, void* y, void* stream);
+
 /* Weight gradient of the same layer (training path, __main__.py:231-269 backward of every nn.Conv2d):
  * dw[Cout][kh][kw][Cin] (f32) += sum over output pixels of dz[N,Ho,Wo,Cout]^T * x[N,H,W,Cin] (both bf16 NHWC);
  * accumulates into dw (zero it first).  desc.impl: 0 = auto, 1 = tcgen05 (MN-major operands), 2 = mma.sync. */

@@ -148,3 +148,15 @@ extern "C" int nbc_conv_wgrad_bf16(const nbc_conv_desc* d, const void* dz, const
   set_error("nbc_conv_wgrad_bf16: unknown impl %d", d->impl);
   return NBC_ERR_INVALID;
 }
+
+extern "C" int nbc_conv_dual_bf16(const nbc_conv_desc* d, const void* x, const nbc_conv_desc* d2, const void* x2, const void* w_cat,
+                                  const float* bias, void* y, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  NBC_REQUIRE(d && d2 && x && x2 && w_cat && bias && y, "nbc_conv_dual_bf16: null pointer");
+  ConvGeom g{d->N, d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, d->stride, d->pad, d->dil, d->relu, d->f16 ? 1 : 0};
+  ConvGeom g2{d2->N, d2->H, d2->W, d2->Cin, d2->Cout, d2->kh, d2->kw, d2->stride, d2->pad, d2->dil, 0, d->f16 ? 1 : 0};
+  ConvTcPrepared prep;
+  int rc = conv_tc_prepare_dual(g, x, g2, x2, w_cat, bias, y, &prep);
+  if (rc) return rc;
+  return conv_tc_run(&prep, stream);
+}

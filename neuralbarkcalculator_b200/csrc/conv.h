@@ -25,6 +25,9 @@ bool conv_tc_supported(const ConvGeom& g);
 // valid_h (device, int[N], optional): ragged batch -- valid OUTPUT rows per image (see conv_tc.cu)
 int conv_tc_prepare(const ConvGeom& g, const void* x, const void* w, const float* bias, const void* residual, void* y,
                     ConvTcPrepared* out, const int* valid_h = nullptr);
+// main convolution + a 1x1 convolution of a second tensor accumulated into the same output (see conv_tc.cu)
+int conv_tc_prepare_dual(const ConvGeom& g, const void* x, const ConvGeom& g2, const void* x2, const void* w_cat,
+                         const float* bias, void* y, ConvTcPrepared* out, const int* valid_h = nullptr);
 int conv_tc_run(const ConvTcPrepared* prep, cudaStream_t stream);
 // stem 7x7/2 as an implicit GEMM over the padded bf16 image (see stem.cu)
 int conv_tc_prepare_stem(int N, int Ho, int Wo, int Hp, int Wp, const void* padded, const void* w224, const float* bias,

@@ -35,6 +35,10 @@ struct ConvTcParams {
   int tw_log2, th, tw, tiles_w, tiles_h;
   int num_m_tiles, num_n_tiles;
   int n_taps, cblocks;
+  // optional SECOND operand source accumulated into the same tile (a 1x1 convolution of another tensor: the
+  // downsample branch of a bottleneck fused into its conv3): cblocks2 K blocks read through tmA[map2] at the tile's own
+  // pixel coordinates, after the taps of the main source; its weights follow the main ones along K.  0 = none.
+  int cblocks2, map2;
   int relu;
   int f16;  // operand / output format: 0 bf16, 1 fp16
   // ragged batches: valid_h[img] = number of valid OUTPUT rows of image img (nullptr: all rows valid).  Rows at or
@@ -153,7 +157,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int kblocks = p.n_taps * p.cblocks;
+  const int kblocks = p.n_taps * p.cblocks + p.cblocks2;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -176,6 +180,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
               stage = 0;
               phase ^= 1u;
             }
+          }
+        }
+        for (int cb = 0; cb < p.cblocks2; ++cb) {   // second source (fused downsample branch)
+          mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + (int)stage);
+          uint8_t* sA = smem + stage * Cfg::kStageBytes;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_4d(sA, &p.tmA[p.map2], &full_bar[stage], cb * KBLK, t.w0, t.h0, t.img);
+          tma_load_2d(sA + kABytes, &p.tmB, &full_bar[stage], (p.n_taps * p.cblocks + cb) * KBLK, n0);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
       }
@@ -611,6 +626,43 @@ int conv_tc_prepare(const ConvGeom& g, const void* x, const void* w, const float
   int rc = build_launch(g, x, w, bias, residual, y, L);
   L->p.valid_h = valid_h;
   return rc;
+}
+
+// y = act(conv(x; w[:, :K1]) + conv1x1(x2; w[:, K1:]) + bias): g is the main convolution (stride 1), g2 a 1x1 convolution
+// (stride 1 or 2, no padding) of a second tensor with the same output geometry; w = the two packed weight matrices
+// concatenated along K per output channel.  One accumulator, one epilogue, no intermediate tensor.
+int conv_tc_prepare_dual(const ConvGeom& g, const void* x, const ConvGeom& g2, const void* x2, const void* w_cat,
+                         const float* bias, void* y, ConvTcPrepared* out, const int* valid_h) {
+  if (!conv_tc_supported(g) || !conv_tc_supported(g2) || g.stride != 1 || g2.kh != 1 || g2.kw != 1 || g2.pad != 0 ||
+      g2.Cout != g.Cout || g2.N != g.N || g2.Ho() != g.Ho() || g2.Wo() != g.Wo()) {
+    set_error("conv_tc_prepare_dual: unsupported pair (main %dx%d k%d s%d, second Cin=%d k%d s%d)", g.Cin, g.Cout, g.kh, g.stride,
+              g2.Cin, g2.kh, g2.stride);
+    return NBC_ERR_INVALID;
+  }
+  if ((reinterpret_cast<uintptr_t>(bias) & 15) != 0) {
+    set_error("conv_tc: bias must be 16-byte aligned");
+    return NBC_ERR_INVALID;
+  }
+  ConvTcLaunch* L = reinterpret_cast<ConvTcLaunch*>(out->storage);
+  int rc = build_launch(g, x, w_cat, bias, nullptr, y, L);
+  if (rc) return rc;
+  ConvTcParams& p = L->p;
+  p.valid_h = valid_h;
+  const uint64_t eb = 2;
+  const char* xb = reinterpret_cast<const char*>(x2);
+  p.map2 = 1;        // the main source is a stride-1 convolution: it only uses tmA[0]
+  p.cblocks2 = g2.Cin / 64;
+  if (g2.stride == 1)
+    rc = encode_act_map(&p.tmA[1], xb, g2.Cin, g2.W, g2.H, g2.N, (uint64_t)g2.Cin * eb, (uint64_t)g2.W * g2.Cin * eb,
+                        (uint64_t)g2.H * g2.W * g2.Cin * eb, p.tw, p.th);
+  else   // stride 2, no padding: the even / even lattice of the input
+    rc = encode_act_map(&p.tmA[1], xb, g2.Cin, (uint64_t)(g2.W + 1) / 2, (uint64_t)(g2.H + 1) / 2, g2.N, 2ull * g2.Cin * eb,
+                        2ull * g2.W * g2.Cin * eb, (uint64_t)g2.H * g2.W * g2.Cin * eb, p.tw, p.th);
+  if (rc) return rc;
+  rc = encode_weight_map(&p.tmB, w_cat, (uint64_t)p.n_taps * g.Cin + g2.Cin, g.Cout, L->block_n);
+  if (rc) return rc;
+  L->out_bufs = (p.n_taps * p.cblocks + p.cblocks2 <= 8) ? 4 : 2;
+  return 0;
 }
 
 int conv_tc_run(const ConvTcPrepared* prep, cudaStream_t stream) {

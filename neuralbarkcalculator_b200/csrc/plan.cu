@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "conv.h"
+#include "train.h"   // axpby
 
 namespace nbc {
 
@@ -24,6 +25,9 @@ struct ConvLayer {
 struct Block {
   ConvLayer c1, c2, c3, ds;
   bool has_ds = false;
+  // conv3 and the downsample branch as ONE launch (tcgen05 path): weights [Cout][K3 + Kds], bias = b3 + bds
+  __nv_bfloat16* w_cat = nullptr;
+  float* bias_cat = nullptr;
 };
 
 struct Step {  // one launch of the cached forward
@@ -36,6 +40,7 @@ struct Step {  // one launch of the cached forward
   void* y;
   ConvTcPrepared prep;
   const char* name;
+  double extra_flops = 0.0;   // fused second source
 };
 
 }  // namespace nbc
@@ -95,6 +100,15 @@ static int make_conv(nbc_plan* p, const void* const* t, int Cin, int Cout, int k
                    reinterpret_cast<const float*>(t[2]), reinterpret_cast<const float*>(t[3]),
                    reinterpret_cast<const float*>(t[4]), nullptr, 1e-5f, Cout, Cin, k, k, Cin, L->w, nullptr, L->bias, 0,
                    p->f16);
+}
+
+// [W3 | Wds] per output channel and b3 + bds, for the fused conv3 + downsample launch
+static int concat_weights(Block& B, int width, int inplanes, int outp) {
+  const size_t pitch = (size_t)(width + inplanes) * 2;
+  NBC_CUDA(cudaMemcpy2DAsync(B.w_cat, pitch, B.c3.w, (size_t)width * 2, (size_t)width * 2, outp, cudaMemcpyDeviceToDevice, 0));
+  NBC_CUDA(cudaMemcpy2DAsync(reinterpret_cast<char*>(B.w_cat) + (size_t)width * 2, pitch, B.ds.w, (size_t)inplanes * 2,
+                             (size_t)inplanes * 2, outp, cudaMemcpyDeviceToDevice, 0));
+  return axpby(B.c3.bias, 1.f, B.ds.bias, 1.f, outp, B.bias_cat, 0);
 }
 
 struct Dims {
@@ -203,7 +217,24 @@ static int build_steps(nbc_plan* p, int N, int H, int W, void* workspace, bool r
     rc = add_conv(p, B.c2, N, h1, w1, t1, nullptr, t2, "conv2", &h2, &w2, levels, &lv);
     if (rc) return rc;
     level = lv;
-    if (B.has_ds) {
+    if (B.has_ds && p->impl != 2) {
+      // conv3 + downsample branch in one launch: out = relu(W3 * t2 + Wds * in(strided) + b3 + bds); no intermediate
+      // tensor for the branch, its 1x1 convolution is just more K for the same accumulator
+      Step s;
+      memset(&s.prep, 0, sizeof(s.prep));
+      s.g = ConvGeom{N, h2, w2, B.c3.Cin, B.c3.Cout, 1, 1, 1, 0, 1, 1, p->f16};
+      const ConvGeom g2{N, h, w, B.ds.Cin, B.ds.Cout, 1, 1, B.ds.stride, 0, 1, 0, p->f16};
+      s.extra_flops = g2.flops();
+      s.x = t2, s.w = B.w_cat, s.bias = B.bias_cat, s.residual = nullptr, s.y = other, s.name = "conv3+downsample";
+      s.kind = 2;
+      rc = conv_tc_prepare_dual(s.g, t2, g2, in, B.w_cat, B.bias_cat, other, &s.prep, levels != nullptr ? levels + (size_t)lv * N : nullptr);
+      if (rc) return rc;
+      h3 = s.g.Ho(), w3 = s.g.Wo();
+      p->steps_ptr->push_back(s);
+      void* tmp = in;
+      in = other;
+      other = tmp;
+    } else if (B.has_ds) {
       int hd, wd;
       rc = add_conv(p, B.ds, N, h, w, in, nullptr, other, "downsample", &hd, &wd, levels, &lv_in);
       if (rc) return rc;
@@ -342,6 +373,10 @@ extern "C" nbc_plan* nbc_plan_create(const void* const* t, int n_tensors, const 
         B.has_ds = true;
         if (!rc) rc = make_conv(p, t + idx, inplanes, outp, 1, s, 0, 1, 0, &B.ds);
         idx += 6;
+        // fused launch: [W3 | Wds] along K (both already carry their BN scale), bias = b3 + bds
+        if (!rc) rc = dev_alloc(p, reinterpret_cast<void**>(&B.w_cat), (size_t)outp * (width + inplanes) * 2);
+        if (!rc) rc = dev_alloc(p, reinterpret_cast<void**>(&B.bias_cat), (size_t)outp * 4);
+        if (!rc) rc = concat_weights(B, width, inplanes, outp);
       }
       inplanes = outp;
       p->blocks.push_back(B);
@@ -439,7 +474,7 @@ extern "C" int nbc_plan_profile(nbc_plan* p, const void* input, int input_kind, 
   NBC_CUDA(cudaStreamSynchronize(stream));
   for (int i = 0; i < n; ++i) {
     NBC_CUDA(cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]));
-    if (flops_out) flops_out[i] = (steps[i].kind == 1) ? 0.0 : steps[i].g.flops();
+    if (flops_out) flops_out[i] = (steps[i].kind == 1) ? 0.0 : steps[i].g.flops() + steps[i].extra_flops;
   }
   for (auto& e : ev) cudaEventDestroy(e);
   return n;

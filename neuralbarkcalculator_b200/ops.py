@@ -118,6 +118,27 @@ def conv_bf16(x, w_packed, bias, stride=1, pad=0, dil=1, relu=False, residual=No
     return y
 
 
+def conv_dual_bf16(x, w, x2, w2, bias, stride2=1, relu=True):
+    """y = act(conv1x1(x; w) + conv1x1(x2; w2, stride2) + bias) in one launch (a bottleneck's conv3 + downsample branch).
+    x [N,H,W,C1], w [Cout,1,1,C1]; x2 [N,H2,W2,C2], w2 [Cout,1,1,C2] (bf16|fp16, BN folded); bias f32 [Cout] = sum of both."""
+    lib = _lib.load()
+    x, f16 = _half(x, 'x')
+    x2 = _contig(x2, x.dtype, 'x2')
+    w, w2 = _contig(w, x.dtype, 'w'), _contig(w2, x.dtype, 'w2')
+    bias = _contig(bias, torch.float32, 'bias')
+    N, H, W, C1 = x.shape
+    _, H2, W2, C2 = x2.shape
+    Cout = w.shape[0]
+    w_cat = torch.cat([w.reshape(Cout, C1), w2.reshape(Cout, C2)], dim=1).contiguous()
+    with torch.cuda.device(x.device):
+        y = torch.empty((N, H, W, Cout), dtype=x.dtype, device=x.device)
+        d = _lib.ConvDesc(N, H, W, C1, Cout, 1, 1, 1, 0, 1, 1 if relu else 0, 1, f16)
+        d2 = _lib.ConvDesc(N, H2, W2, C2, Cout, 1, 1, stride2, 0, 1, 0, 1, f16)
+        _lib.check(lib.nbc_conv_dual_bf16(C.byref(d), _ptr(x), C.byref(d2), _ptr(x2), _ptr(w_cat), _ptr(bias), _ptr(y),
+                                          _stream(x.device)), 'nbc_conv_dual_bf16')
+    return y
+
+
 def conv_wgrad_bf16(dz, x, kh, kw, stride=1, pad=0, dil=1, impl=0, out=None):
     """Weight gradient of conv_bf16: dz bf16 NHWC [N,Ho,Wo,Cout], x bf16 NHWC [N,H,W,Cin] -> f32 [Cout,kh,kw,Cin]
     (accumulated into ``out`` when given).  impl 0 auto, 1 tcgen05, 2 mma.sync."""

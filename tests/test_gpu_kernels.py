@@ -174,6 +174,32 @@ def test_conv_tc_many_tiles(cuda_device):
     _conv_case(cuda_device, 64, 64, 3, 1, 1, N=2, H=96, W=256, relu=True, use_res=False, impl=1, seed=6)
 
 
+@pytest.mark.parametrize('shape', [(64, 64, 256, 1), (128, 256, 512, 2), (256, 512, 1024, 1), (512, 1024, 2048, 1)])
+def test_conv_dual_source(cuda_device, shape):
+    """conv3 + downsample branch of a bottleneck's first block as ONE launch (two operand sources, one accumulator)
+    against the two separate f32 convolutions on the same bf16 operands."""
+    ops = _ops()
+    C1, C2, Cout, stride2 = shape
+    g = torch.Generator().manual_seed(C1 + stride2)
+    N, H, W = 2, 27, 40
+    H2, W2 = (H * 2 - 1, W * 2 - 1) if stride2 == 2 else (H, W)        # odd input size: the lattice has a ragged edge
+    x = torch.randn(N, H, W, C1, generator=g).to(torch.bfloat16)
+    x2 = torch.randn(N, H2, W2, C2, generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cout, 1, 1, C1, generator=g) / np.sqrt(C1)).to(torch.bfloat16)
+    w2 = (torch.randn(Cout, 1, 1, C2, generator=g) / np.sqrt(C2)).to(torch.bfloat16)
+    bias = torch.randn(Cout, generator=g)
+    y = ops.conv_dual_bf16(x.to(cuda_device), w.to(cuda_device), x2.to(cuda_device), w2.to(cuda_device), bias.to(cuda_device),
+                           stride2=stride2, relu=True)
+    torch.cuda.synchronize()
+    F = torch.nn.functional
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2)) \
+        + F.conv2d(x2.float().permute(0, 3, 1, 2), w2.float().permute(0, 3, 1, 2), stride=stride2) + bias.view(1, -1, 1, 1)
+    ref = ref.relu().permute(0, 2, 3, 1)
+    err = (y.float().cpu() - ref).abs()
+    tol = 2.0 ** -7 * ref.abs() + 2e-2
+    assert not (err > tol).any(), 'max err %.4g bad=%d' % (err.max(), int((err > tol).sum()))
+
+
 # ------------------------------------------------------------------------------------------------- weight gradient
 def _wgrad_case(dev, Cin, Cout, k, stride, dil, N, H, W, impl, seed=0):
     """dW of one conv layer vs torch's own f32 conv weight gradient on the same bf16-rounded operands."""

@@ -11,7 +11,7 @@ import neuralbarkcalculator_b200 as nbc  # noqa: E402
 from oracle import model as omodel, synth  # noqa: E402
 
 
-def layer_names():
+def layer_names(fused=True):
     names = ['stem 3->64 k7 s2', 'maxpool']
     inpl = 64
     for li, (nb, planes) in enumerate(zip((3, 4, 6, 3), (64, 128, 256, 512))):
@@ -19,9 +19,10 @@ def layer_names():
             pre = 'layer%d.%d.' % (li + 1, b)
             names.append(pre + 'conv1 %d->%d k1' % (inpl, planes))
             names.append(pre + 'conv2 %d->%d k3' % (planes, planes))
-            if b == 0:
+            if b == 0 and not fused:
                 names.append(pre + 'downsample %d->%d k1' % (inpl, planes * 4))
-            names.append(pre + 'conv3 %d->%d k1' % (planes, planes * 4))
+            names.append(pre + ('conv3+downsample %d+%d->%d' % (planes, inpl, planes * 4) if (b == 0 and fused) else
+                                'conv3 %d->%d k1' % (planes, planes * 4)))
             inpl = planes * 4
     names += ['head conv3x3 2048->512', 'head 1x1 512->3']
     return names
@@ -47,7 +48,7 @@ def main():
     runs = [plan.profile(img) for _ in range(5)]
     ms = np.median(np.array([[r[0] for r in run] for run in runs]), axis=0)
     fl = [r[1] for r in runs[0]]
-    names = layer_names()
+    names = layer_names(fused=(impl != 2))
     assert len(names) == len(ms), (len(names), len(ms))
     print('N=%d H=%d W=%d impl=%d' % (N, H, W, impl))
     tot = 0.0
