@@ -11,9 +11,14 @@ K1 resize+trim -> FCN-ResNet50 (bf16, tcgen05) -> K3 upsample+argmax -> K5 regio
           collected every step; step k+1 is submitted before step k is collected, as a folder-sized predict run does,
           so the PCIe link (the end-to-end bound) stays busy across steps
 workload batch32 (configs[2]): model-only, u8 [32,1024,1024,3] -> mask + counts.
+workload train (configs[3]): one training step (train-mode forward, weighted CE, backward, NCCL all-reduce, Adam), batch 8
+per GPU at 1024^2; roofline = conv FLOPs of the step / whole step time; e2e = images + targets from pinned host memory,
+loss read back every step.
+workload cli (configs[1] literally): predict.py ROOT --exclude_nodes on a folder of 4096^2 BMP files on tmpfs, every output
+file written; wall clock.
 --impl reference times the CPU oracle (restated reference path, torch CPU f32 with all host threads) on a bounded
-sample: one image per step.  Multi-GPU: one process per GPU (torchrun), images sharded, no collective on the data
-path; time = max over ranks."""
+sample: one image per step (predict) / one 512^2 crop (train).  Multi-GPU: one process per GPU (torchrun), images sharded,
+no collective on the data path; time = max over ranks."""
 import argparse
 import json
 import os
