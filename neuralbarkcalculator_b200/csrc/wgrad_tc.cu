@@ -13,6 +13,8 @@
 //     tensor maps as the forward operand (zero fill outside the image = the conv padding)
 //   * f32 accumulator in TMEM; epilogue = red.global.add.v4.f32 into the f32 gradient buffer
 // Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue.
+#include <algorithm>
+
 #include "common.cuh"
 #include "conv.h"
 #include "train.h"
@@ -295,9 +297,11 @@ int wgrad_tc(const ConvGeom& g, const void* dz, const void* x, float* dw, cudaSt
         if (rc) return rc;
       }
   }
-  // split-K over the pixel tiles: about four CTAs per SM in total, each with at least 16 K blocks
+  // split-K over the pixel tiles, each split with at least 16 K blocks
   const int base_items = p.co_tiles * p.ci_tiles * p.taps;
-  int splits = ceil_div(sm_count() * 4, base_items);
+  // one wave: as many splits as fit the SMs once.  More, smaller splits balance better but every split adds a full tile
+  // of f32 atomics to the same gradient block (4x oversubscription cost 6 % of the training step)
+  int splits = std::max(1, sm_count() / base_items);
   const int max_splits = ceil_div(p.num_pix_tiles, 16);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
