@@ -85,12 +85,14 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_partial(const uint4* __re
   }
 }
 
-// warp-wide sum of the per-block partials of one channel (two values), in double
+// block-wide sum (128 threads, one block per channel) of the per-block partials of one channel (two values), in double,
+// in a fixed order; every thread returns the totals
+constexpr int kBnFinThreads = 128;
 __device__ __forceinline__ void bn_sum_partials(const float* __restrict__ partial, int nblocks, int C, int c, double& s,
                                                 double& q) {
-  const int lane = threadIdx.x & 31;
+  __shared__ double sh[2][kBnFinThreads / 32];
   s = 0.0, q = 0.0;
-  for (int i = lane; i < nblocks; i += 32) {
+  for (int i = threadIdx.x; i < nblocks; i += kBnFinThreads) {
     const float2 v = __ldg(reinterpret_cast<const float2*>(partial + ((int64_t)i * C + c) * 2));
     s += (double)v.x, q += (double)v.y;
   }
@@ -99,20 +101,24 @@ __device__ __forceinline__ void bn_sum_partials(const float* __restrict__ partia
     s += __shfl_xor_sync(0xffffffffu, s, o);
     q += __shfl_xor_sync(0xffffffffu, q, o);
   }
+  if ((threadIdx.x & 31) == 0) sh[0][threadIdx.x >> 5] = s, sh[1][threadIdx.x >> 5] = q;
+  __syncthreads();
+  s = 0.0, q = 0.0;
+#pragma unroll
+  for (int w = 0; w < kBnFinThreads / 32; ++w) s += sh[0][w], q += sh[1][w];
 }
 
-// one warp per channel: sums the partials in double, produces the affine a = gamma*invstd, b = beta - mean*a,
+// one block per channel: sums the partials in double, produces the affine a = gamma*invstd, b = beta - mean*a,
 // saves mean / invstd for the backward and updates the running statistics like torch (momentum, unbiased var)
-__global__ void __launch_bounds__(256) bn_stats_finalize(const float* __restrict__ partial, int nblocks, int C, int64_t M,
+__global__ void __launch_bounds__(kBnFinThreads) bn_stats_finalize(const float* __restrict__ partial, int nblocks, int C, int64_t M,
                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                                   float* __restrict__ running_mean, float* __restrict__ running_var,
                                   float* __restrict__ save_mean, float* __restrict__ save_invstd, float* __restrict__ a_out,
                                   float* __restrict__ b_out) {
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (c >= C) return;
+  const int c = blockIdx.x;
   double s, q;
   bn_sum_partials(partial, nblocks, C, c, s, q);
-  if ((threadIdx.x & 31) != 0) return;
+  if (threadIdx.x != 0) return;
   const double mean = s / (double)M;
   double var = q / (double)M - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -201,15 +207,14 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_partial(const uint4* __rest
   }
 }
 
-// one warp per channel: sums[c] = (s1, s2); accumulates dgamma += s2, dbeta += s1
-__global__ void __launch_bounds__(256) bn_bwd_finalize(const float* __restrict__ partial, int nblocks, int C,
+// one block per channel: sums[c] = (s1, s2); accumulates dgamma += s2, dbeta += s1
+__global__ void __launch_bounds__(kBnFinThreads) bn_bwd_finalize(const float* __restrict__ partial, int nblocks, int C,
                                                        float* __restrict__ sums, float* __restrict__ dgamma,
                                                        float* __restrict__ dbeta) {
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (c >= C) return;
+  const int c = blockIdx.x;
   double s, t;
   bn_sum_partials(partial, nblocks, C, c, s, t);
-  if ((threadIdx.x & 31) != 0) return;
+  if (threadIdx.x != 0) return;
   sums[2 * c] = (float)s, sums[2 * c + 1] = (float)t;
   dgamma[c] += (float)t;
   dbeta[c] += (float)s;
@@ -470,7 +475,7 @@ int bn_forward_train(const void* z, int64_t M, int C, const float* gamma, const 
   const int64_t rpb = ceil_div64(M, nb);
   bn_stats_partial<<<nb, kBnThreads, 0, stream>>>(reinterpret_cast<const uint4*>(z), M, C, rpb, partial);
   NBC_CHECK_LAUNCH();
-  bn_stats_finalize<<<ceil_div(C, 8), 256, 0, stream>>>(partial, nb, C, M, gamma, beta, eps, momentum, running_mean,
+  bn_stats_finalize<<<C, kBnFinThreads, 0, stream>>>(partial, nb, C, M, gamma, beta, eps, momentum, running_mean,
                                                         running_var, save_mean, save_invstd, a, b);
   NBC_CHECK_LAUNCH();
   const int64_t total8 = M * C / 8;
@@ -491,7 +496,7 @@ int bn_backward(const void* dy, const void* y, const void* z, int64_t M, int C, 
                                                 reinterpret_cast<const uint4*>(z), save_mean, save_invstd, M, C, relu, rpb,
                                                 partial);
   NBC_CHECK_LAUNCH();
-  bn_bwd_finalize<<<ceil_div(C, 8), 256, 0, stream>>>(partial, nb, C, sums, dgamma, dbeta);
+  bn_bwd_finalize<<<C, kBnFinThreads, 0, stream>>>(partial, nb, C, sums, dgamma, dbeta);
   NBC_CHECK_LAUNCH();
   const int64_t total8 = M * C / 8;
   bn_bwd_apply_kernel<<<grid_for(total8), 256, 0, stream>>>(
