@@ -5,7 +5,7 @@ import os
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from neuralbarkcalculator_b200 import ops  # noqa: E402
 
 

@@ -2,7 +2,7 @@
 import os, sys
 import numpy as np
 import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import model as omodel, synth, losses as olosses
 from neuralbarkcalculator_b200.train import Trainer
 
