@@ -103,6 +103,9 @@ class SimpleSegmentationModel(nn.Module):
         return ops.upsample_argmax(low, (images_u8.shape[1], images_u8.shape[2]))
 
 
+_DUAL_LUT = np.array([0, 127, 255] + [0] * 253, dtype=np.uint8)
+
+
 def fcn_resnet50(pretrained=True, dropout=0.1):
     """models.py:127-139.  ``pretrained=True`` needs torchvision's ImageNet weights (a download)."""
     weights = None
@@ -243,7 +246,7 @@ class NeuralBarkCalculator():
                 _, _, fname, wood_type = dataset.samples[i]
                 img = torch.from_numpy(np.ascontiguousarray(fut.result())).to(self.device)
                 mask, counts = self.predict_array(img, excludes_nodes)
-                dual = torch.where(mask == 1, 127, torch.where(mask == 2, 255, 0)).to(torch.uint8).cpu().numpy()
+                dual = _DUAL_LUT[mask.cpu().numpy()]          # models.py:349-353: classes 0 / 1 / 2 -> 0 / 127 / 255
                 results_csv.append([fname, wood_type] + self._stats_strings(counts.tolist(), mask.numel()))
                 saves.append(pool.submit(lambda a, d: Image.fromarray(a, mode='L').save(d), dual,
                                          join(output_path, 'outputs', wood_type, fname)))
