@@ -38,12 +38,14 @@ def combined_image(proc, mask, title):
     left = proc[::2, ::2]
     right = _VIRIDIS3[mask[::2, ::2]]
     h, w = left.shape[:2]
-    canvas = np.full((h + 16, 2 * w + 8, 3), 255, dtype=np.uint8)
+    canvas = np.empty((h + 16, 2 * w + 8, 3), dtype=np.uint8)
     canvas[16:, :w] = left
+    canvas[16:, w:w + 8] = 255
     canvas[16:, w + 8:] = right
-    im = Image.fromarray(canvas)
-    ImageDraw.Draw(im).text((4, 2), title, fill=(0, 0, 0))
-    return np.asarray(im)
+    strip = Image.new('RGB', (2 * w + 8, 16), (255, 255, 255))      # only the title strip goes through PIL
+    ImageDraw.Draw(strip).text((4, 2), title, fill=(0, 0, 0))
+    canvas[:16] = np.asarray(strip)
+    return canvas
 
 
 def bmp_geometry(path):
