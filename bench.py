@@ -292,7 +292,7 @@ def main():
                             'ms_per_step': ms_h / args.steps},
                     'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': tf_peak, 'unit': 'TFLOP/s',
                                  'frac': achieved / tf_peak, 'traffic': None, 'peak_kind': peak_kind + ' (sustained bf16)',
-                                 'kernel': 'conv_tc_kernel (forward + data gradient) and wgrad_tc_kernel: algorithmic conv FLOPs of '
+                                 'kernel': 'conv_tc_kernel / conv_tc_pair_kernel (forward + data gradient) and wgrad_tc_kernel: algorithmic conv FLOPs of '
                                            'the step / WHOLE step time (BatchNorm, loss, Adam and the all-reduce included), i.e. a '
                                            'lower bound on the kernels\' own rate'},
                     'cpu_baseline': cpu_base}
@@ -426,11 +426,11 @@ def main():
             tensor_pct = tj.get('conv_tc_tensor_pipe_active_pct_time_weighted')
         roof = {'bound': 'tensor', 'achieved': achieved, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf_peak,
                 'traffic': traffic, 'peak_kind': peak_kind + ' (sustained bf16)',
-                'kernel': 'conv_tc_kernel: the %d tensor-core conv launches of one network pass over a chunk of %d scans '
+                'kernel': 'conv_tc_kernel / conv_tc_pair_kernel (CTA pairs, cta_group::2): the %d tensor-core conv launches of one network pass over a chunk of %d scans '
                           '(dense [%d,624,1024,3] batch = mean trimmed height; each first bottleneck runs conv3 + downsample '
                           'as one launch), per-launch CUDA events, median of 3; achieved = sum of algorithmic FLOPs / sum of '
                           'launch durations' % (len(conv), chunk, chunk),
-                'tensor_pipe_active_pct_ncu': tensor_pct,      # time-weighted over the same 53 launches (profiles/r01i_*)
+                'tensor_pipe_active_pct_ncu': tensor_pct,      # time-weighted over the same launches (profiles/ncu_traffic.json)
                 'flops_per_launch_avg': conv_fl / len(conv), 'ms_per_launch_avg': conv_ms / len(conv),
                 'conv_share_of_forward': conv_ms / tot_ms, 'forward_ms_per_image': tot_ms / chunk}
         if not args.no_cpu_baseline and world == 1:

@@ -18,6 +18,8 @@
 //     place, so residual reads and output writes are full 128-byte lines issued by the copy engine, not by the LSU.
 // Persistent CTAs (one per SM), warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..9 = epilogue,
 // 10 = output / residual TMA.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "conv.h"
 
@@ -372,6 +374,311 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cluster of 2, tcgen05 cta_group::2).  One MMA of M = 256 spans the two SMs of a TPC: CTA r of the
+// pair owns M tile 2*m_pair + r (its own 128 pixels of A, its own 128 TMEM lanes, its own epilogue / output TMA) and
+// stages only HALF of the weight tile (BN/2 rows of B) -- 32 KB instead of 48 KB of shared-memory fill per K block
+// at BN = 256, so the same shared memory holds 6 operand stages instead of 4.  The leader (rank 0) issues every MMA;
+// "stage full" barriers live in the leader (both CTAs' TMA loads count their bytes there), "stage empty" and
+// "accumulator full" are multicast by tcgen05.commit to both CTAs, "accumulator empty" is arrived remotely by the
+// peer's epilogue warps.  A pair is skipped in a ragged batch only when BOTH of its tiles are dead; an M tile beyond
+// the last one (odd tile count) is a phantom: its loads are zero-filled and its stores dropped by the TMA unit.
+// ------------------------------------------------------------------------------------------------------------
+template <int BN, int OB>
+struct TcCfgPair {
+  static constexpr int kABytes = 128 * 64 * 2;
+  static constexpr int kBBytes = (BN / 2) * 64 * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kFixedBytes = OB * kOutBufBytes + 256 /*barriers*/ + 1024 /*align slack*/;
+  static constexpr int kStagesFit = (kSmemLimit - kFixedBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit < 8 ? kStagesFit : 8;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kFixedBytes;
+  static constexpr int kSteps = BN / 64;
+  static constexpr int kWarpsPerStep = 4;
+  static_assert(BN == 128 || BN == 256, "pair kernel: BN = 128 or 256");
+  static_assert(kStages >= 2 && kSmemBytes <= kSmemLimit && kSmemBytes > 120 * 1024, "shared memory budget");
+  static_assert((2 * kStages + 4 + 2 * OB) * 8 + 4 <= 256, "barrier block");
+};
+
+__device__ __forceinline__ bool mtile_dead(const ConvTcParams& p, int m_tile) {
+  if (m_tile >= p.num_m_tiles) return true;
+  if (p.valid_h == nullptr) return false;
+  const int mt = m_tile / p.tiles_w;
+  return (mt % p.tiles_h) * p.th >= __ldg(p.valid_h + mt / p.tiles_h);
+}
+__device__ __forceinline__ bool pair_dead(const ConvTcParams& p, int pair_tile) {
+  const int mp = pair_tile / p.num_n_tiles;
+  return mtile_dead(p, 2 * mp) && mtile_dead(p, 2 * mp + 1);
+}
+// this CTA's tile (single-CTA numbering) of a pair tile
+__device__ __forceinline__ int pair_my_tile(const ConvTcParams& p, int pair_tile, int rank) {
+  return (2 * (pair_tile / p.num_n_tiles) + rank) * p.num_n_tiles + pair_tile % p.num_n_tiles;
+}
+
+template <int BN, int OB, bool RES, bool RELU, bool F16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+    conv_tc_pair_kernel(const __grid_constant__ ConvTcParams p) {
+  using Cfg = TcCfgPair<BN, OB>;
+  constexpr int kABytes = Cfg::kABytes;
+  constexpr int kSteps = Cfg::kSteps;
+  extern __shared__ uint8_t smem_raw[];
+  // the dynamic shared window starts at the same offset in both CTAs (same kernel, no static shared memory), so the
+  // aligned buffers and barriers sit at identical offsets -- which cta_group::2 MMA descriptors and multicast commits need
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* obuf = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(obuf + OB * kOutBufBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tfull_bar = empty_bar + Cfg::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* bufready_bar = tempty_bar + 2;
+  uint64_t* outready_bar = bufready_bar + OB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(outready_bar + OB);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 2);    // the two producers (used in the leader only)
+      mbar_init(&empty_bar[i], 1);   // multicast commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);   // multicast commit
+      mbar_init(&tempty_bar[i], 16); // 8 epilogue warps of each CTA (used in the leader only)
+    }
+    for (int i = 0; i < OB; ++i) {
+      mbar_init(&bufready_bar[i], 1);
+      mbar_init(&outready_bar[i], Cfg::kWarpsPerStep);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 10 && lane == 0) {
+    tma_prefetch_desc(&p.tmOut);
+    if (RES) tma_prefetch_desc(&p.tmRes);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int total_pairs = ((p.num_m_tiles + 1) >> 1) * p.num_n_tiles;
+  const int kblocks = p.n_taps * p.cblocks + p.cblocks2;
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t full0 = mapa_shared(smem_u32(&full_bar[0]), 0);   // the leader's full barriers
+      for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+        if (pair_dead(p, pt)) continue;
+        const TileCoord t = tile_coord(p, pair_my_tile(p, pt, rank));
+        const int n0 = t.n_tile * BN + rank * (BN / 2);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const CUtensorMap* mA;
+          int c0, cw, ch;
+          if (kb < p.n_taps * p.cblocks) {
+            const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+            mA = &p.tmA[p.tap_map[tap]];
+            c0 = cb * 64, cw = t.w0 + p.tap_dw[tap], ch = t.h0 + p.tap_dh[tap];
+          } else {   // second source (fused downsample branch)
+            mA = &p.tmA[p.map2];
+            c0 = (kb - p.n_taps * p.cblocks) * 64, cw = t.w0, ch = t.h0;
+          }
+          mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + (int)stage);
+          uint8_t* sA = smem + stage * Cfg::kStageBytes;
+          const uint32_t fb = full0 + stage * 8u;
+          if (leader)
+            mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          else
+            mbar_arrive_cluster(fb);
+          tma_load_4d_pair(sA, mA, fb, c0, cw, ch, t.img);
+          tma_load_2d_pair(sA + kABytes, &p.tmB, fb, kb * 64, n0);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader only) ================================
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = F16 ? umma_idesc_f16(256, BN) : umma_idesc_bf16(256, BN);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+        if (pair_dead(p, pt)) continue;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 300 + (int)acc);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 200 + (int)stage);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16_pair(d_tmem, umma_desc_kmajor<128>(a_addr + k * 32), umma_desc_kmajor<128>(b_addr + k * 32), idesc,
+                           (uint32_t)((kb | k) != 0));
+          }
+          umma_commit_pair(&empty_bar[stage], 3);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit_pair(&tfull_bar[acc], 3);
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 10) {
+    // ================================ output / residual TMA (per CTA, own tile) ================================
+    if (elect_one()) {
+      constexpr int kAhead = RES ? OB - 1 : 0;
+      int ld_pt = cluster_id;
+      while (ld_pt < total_pairs && pair_dead(p, ld_pt)) ld_pt += num_clusters;
+      int st_pt = ld_pt, ld_j = 0, st_j = 0;
+      uint32_t ld_s = 0, st_s = 0;
+      auto issue_load = [&]() {
+        const TileCoord t = tile_coord(p, pair_my_tile(p, ld_pt, rank));
+        const uint32_t b = ld_s % OB;
+        mbar_expect_tx(&bufready_bar[b], kOutBufBytes);
+        tma_load_4d(obuf + b * kOutBufBytes, &p.tmRes, &bufready_bar[b], t.n_tile * BN + step_group<kSteps>(ld_j) * 64, t.w0,
+                    t.h0, t.img);
+        ++ld_s;
+        if (++ld_j == kSteps) {
+          ld_j = 0;
+          ld_pt += num_clusters;
+          while (ld_pt < total_pairs && pair_dead(p, ld_pt)) ld_pt += num_clusters;
+        }
+      };
+      if (RES) {
+        for (int i = 0; i < kAhead && ld_pt < total_pairs; ++i) issue_load();
+      }
+      while (st_pt < total_pairs) {
+        if (RES && ld_pt < total_pairs) {
+          tma_store_wait_read<0>();
+          issue_load();
+        }
+        const uint32_t b = st_s % OB;
+        mbar_wait(&outready_bar[b], (st_s / OB) & 1u, 500 + (int)b);
+        const TileCoord t = tile_coord(p, pair_my_tile(p, st_pt, rank));
+        tma_store_4d(&p.tmOut, obuf + b * kOutBufBytes, t.n_tile * BN + step_group<kSteps>(st_j) * 64, t.w0, t.h0, t.img);
+        tma_store_commit();
+        if (!RES) {
+          tma_store_wait_read<0>();
+          mbar_arrive(&bufready_bar[b]);
+        }
+        ++st_s;
+        if (++st_j == kSteps) {
+          st_j = 0;
+          st_pt += num_clusters;
+          while (st_pt < total_pairs && pair_dead(p, st_pt)) st_pt += num_clusters;
+        }
+      }
+      tma_store_wait_all();
+    }
+    __syncwarp();
+  } else {
+    // ================================ epilogue (warps 2..9, per CTA, own 128 TMEM lanes) ================================
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    constexpr int kUnits = 8;
+    constexpr int kMySteps = kSteps / 2;
+    const int row = q * 32 + lane;
+    const uint32_t row_off = (uint32_t)row * 128u;
+    const uint32_t rsw = (uint32_t)(row & 7);
+    const uint32_t tempty0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);   // the leader's accumulator-empty barriers
+    uint32_t acc = 0, acc_phase = 0, live_tiles = 0;
+    for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+      const int tile = pair_my_tile(p, pt, rank);
+      const TileCoord t = tile_coord(p, tile);
+      const bool phantom = t.img >= p.N;
+      const int vh = phantom ? 0 : (p.valid_h != nullptr ? __ldg(p.valid_h + t.img) : INT_MAX);
+      const int h = t.h0 + (row >> p.tw_log2), w = t.w0 + (row & (p.tw - 1));
+      if (pair_dead(p, pt)) {
+        if (!phantom && t.h0 < vh + kRaggedHalo && w < p.Wo && h < p.Ho && h < vh + kRaggedHalo) {
+          constexpr int kColsZ = BN / 2;
+          __nv_bfloat16* o = p.out + (((int64_t)t.img * p.Ho + h) * p.Wo + w) * p.Cout + t.n_tile * BN + half * kColsZ;
+          for (int c = 0; c < kColsZ; c += 8) *reinterpret_cast<uint4*>(o + c) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        continue;
+      }
+      const bool live = h < vh;
+      mbar_wait(&tfull_bar[acc], acc_phase, 400 + (int)acc);
+      tc_fence_after();
+#pragma unroll
+      for (int i = 0; i < kMySteps; ++i) {
+        const int j = half + 2 * i;
+        const int grp = step_group<kSteps>(j);
+        const uint32_t s = live_tiles * kSteps + j;
+        const uint32_t b = s % OB;
+        const int col0 = grp * 64;
+        uint32_t a[kUnits * 8];
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + col0;
+#pragma unroll
+        for (int k = 0; k < kUnits / 4; ++k) tmem_ld32(t_addr + 32 * k, reinterpret_cast<uint32_t(&)[32]>(a[32 * k]));
+        const float* bptr = p.bias + t.n_tile * BN + col0;
+        mbar_wait(&bufready_bar[b], RES ? ((s / OB) & 1u) : (((s / OB) & 1u) ^ 1u), 600 + (int)b);
+        tmem_ld_wait();
+        if (i == kMySteps - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty0 + acc * 8u);
+        }
+        uint8_t* rowp = obuf + b * kOutBufBytes + row_off;
+#pragma unroll
+        for (int u = 0; u < kUnits; ++u) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bptr + u * 8));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bptr + u * 8 + 4));
+          uint4* sp = reinterpret_cast<uint4*>(rowp + ((((uint32_t)u) ^ rsw) << 4));
+          float v[8] = {__uint_as_float(a[u * 8 + 0]) + b0.x, __uint_as_float(a[u * 8 + 1]) + b0.y,
+                        __uint_as_float(a[u * 8 + 2]) + b0.z, __uint_as_float(a[u * 8 + 3]) + b0.w,
+                        __uint_as_float(a[u * 8 + 4]) + b1.x, __uint_as_float(a[u * 8 + 5]) + b1.y,
+                        __uint_as_float(a[u * 8 + 6]) + b1.z, __uint_as_float(a[u * 8 + 7]) + b1.w};
+          if (RES) {
+            const uint4 r4 = *sp;
+            const uint32_t rv[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[2 * k] += lo16(rv[k], F16), v[2 * k + 1] += hi16(rv[k], F16);
+          }
+          if (RELU) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+          }
+          uint4 o = make_uint4(pack16x2(v[0], v[1], F16), pack16x2(v[2], v[3], F16), pack16x2(v[4], v[5], F16),
+                               pack16x2(v[6], v[7], F16));
+          if (!live) o = make_uint4(0u, 0u, 0u, 0u);
+          *sp = o;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&outready_bar[b]);
+      }
+      ++live_tiles;
+      acc ^= 1u;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  // neither CTA may leave while the other can still touch its shared memory / barriers / TMEM
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
 static int encode_act_map(CUtensorMap* m, const void* base, uint64_t C, uint64_t Wd, uint64_t Hd, uint64_t Nd,
@@ -441,7 +748,39 @@ struct ConvTcLaunch {
   int kblk;
   int grid;
   int out_bufs;
+  int pair;   // 1: conv_tc_pair_kernel (clusters of 2, cta_group::2 MMA)
 };
+
+// Which launches run on CTA pairs (conv_tc_pair_kernel).  Measured per layer class on B200 (profiles/r01s_*): pairs win
+// where the operand pipeline or the MMA sets the pace -- Cout % 256 == 0 without a residual and K >= 512 (the 1x1
+// reductions out of wide tensors, the 3x3 convs of layer3 / layer4 / the head, conv3 + downsample of layer3 / layer4) --
+// and lose on the residual layers (epilogue / HBM bound), on BN = 128 and on very short K.
+// Environment NBC_CTA2 overrides the rule for experiments: a bit mask of layer classes (1: 1x1 without residual,
+// 2: residual, 4: 3x3, 8: dual source) forced onto pairs whenever Cout % 128 == 0; 0 switches pairs off.
+static int pair_mode() {
+  static int mode = -2;
+  if (mode == -2) {
+    const char* e = getenv("NBC_CTA2");
+    mode = (e && *e) ? atoi(e) : -1;
+  }
+  return mode;
+}
+static int want_pair(int cls, int bn, int kblocks) {
+  const int mode = pair_mode();
+  if (mode >= 0) return (bn >= 128 && (mode & cls)) ? 1 : 0;
+  return (bn == 256 && cls != 2 && kblocks >= 8) ? 1 : 0;
+}
+static void set_grid(ConvTcLaunch* L) {
+  const ConvTcParams& p = L->p;
+  const int sms = sm_count();
+  if (L->pair) {
+    const int pairs = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+    L->grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);
+  } else {
+    const int total = p.num_m_tiles * p.num_n_tiles;
+    L->grid = total < sms ? total : sms;
+  }
+}
 
 // output (and residual) as [N][Ho][Wo][Cout] with the box of one 64-channel group of a tile
 static int encode_out_maps(ConvTcParams* p, int N, int Ho, int Wo, int Cout, const void* y, const void* residual) {
@@ -530,14 +869,13 @@ static int build_launch(const ConvGeom& g, const void* x, const void* w, const f
     // the prefetch in the kernel touches tmA[0]; make sure it is a valid map
     if (!used[0]) p.tmA[0] = p.tmA[p.tap_map[0]];
   }
-  int rc = encode_weight_map(&p.tmB, w, (uint64_t)p.n_taps * g.Cin, g.Cout, bn);
+  L->pair = want_pair(residual != nullptr ? 2 : (p.n_taps > 1 ? 4 : 1), bn, p.n_taps * p.cblocks);
+  int rc = encode_weight_map(&p.tmB, w, (uint64_t)p.n_taps * g.Cin, g.Cout, L->pair ? bn / 2 : bn);
   if (rc) return rc;
   rc = encode_out_maps(&p, g.N, Ho, Wo, g.Cout, y, residual);
   if (rc) return rc;
   L->out_bufs = (residual != nullptr || p.n_taps * p.cblocks <= 8) ? 4 : 2;
-  const int total = p.num_m_tiles * p.num_n_tiles;
-  const int sms = sm_count();
-  L->grid = total < sms ? total : sms;
+  set_grid(L);
   return 0;
 }
 
@@ -552,6 +890,40 @@ static int launch_one(const ConvTcLaunch& L, cudaStream_t stream) {
   conv_tc_kernel<BN, KBLK, OB, RES, RELU, F16><<<L.grid, kTcThreads, TcCfg<BN, KBLK, OB>::kSmemBytes, stream>>>(L.p);
   NBC_CHECK_LAUNCH();
   return 0;
+}
+
+template <int BN, int OB, bool RES, bool RELU, bool F16>
+static int launch_pair_one(const ConvTcLaunch& L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    NBC_CUDA(cudaFuncSetAttribute(conv_tc_pair_kernel<BN, OB, RES, RELU, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  TcCfgPair<BN, OB>::kSmemBytes));
+    attr_set = true;
+  }
+  // __cluster_dims__(2, 1, 1) on the kernel: the grid is a whole number of pairs
+  conv_tc_pair_kernel<BN, OB, RES, RELU, F16><<<L.grid, kTcThreads, TcCfgPair<BN, OB>::kSmemBytes, stream>>>(L.p);
+  NBC_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int BN>
+static int launch_pair(const ConvTcLaunch& L, cudaStream_t stream) {
+  const bool res = L.p.residual != nullptr;
+  const int key = (res ? 8 : (L.out_bufs == 4 ? 4 : 0)) | (L.p.relu ? 2 : 0) | (L.p.f16 ? 1 : 0);
+  switch (key) {
+    case 0: return launch_pair_one<BN, 2, false, false, false>(L, stream);
+    case 1: return launch_pair_one<BN, 2, false, false, true>(L, stream);
+    case 2: return launch_pair_one<BN, 2, false, true, false>(L, stream);
+    case 3: return launch_pair_one<BN, 2, false, true, true>(L, stream);
+    case 4: return launch_pair_one<BN, 4, false, false, false>(L, stream);
+    case 5: return launch_pair_one<BN, 4, false, false, true>(L, stream);
+    case 6: return launch_pair_one<BN, 4, false, true, false>(L, stream);
+    case 7: return launch_pair_one<BN, 4, false, true, true>(L, stream);
+    case 8: return launch_pair_one<BN, 4, true, false, false>(L, stream);
+    case 9: return launch_pair_one<BN, 4, true, false, true>(L, stream);
+    case 10: return launch_pair_one<BN, 4, true, true, false>(L, stream);
+    default: return launch_pair_one<BN, 4, true, true, true>(L, stream);
+  }
 }
 
 template <int BN, int KBLK>
@@ -605,9 +977,8 @@ int conv_tc_prepare_stem(int N, int Ho, int Wo, int Hp, int Wp, const void* padd
   rc = encode_out_maps(&p, N, Ho, Wo, 64, y, nullptr);
   if (rc) return rc;
   L->out_bufs = 4;
-  const int total = p.num_m_tiles;
-  const int sms = sm_count();
-  L->grid = total < sms ? total : sms;
+  L->pair = 0;
+  set_grid(L);
   return 0;
 }
 
@@ -659,15 +1030,18 @@ int conv_tc_prepare_dual(const ConvGeom& g, const void* x, const ConvGeom& g2, c
     rc = encode_act_map(&p.tmA[1], xb, g2.Cin, (uint64_t)(g2.W + 1) / 2, (uint64_t)(g2.H + 1) / 2, g2.N, 2ull * g2.Cin * eb,
                         2ull * g2.W * g2.Cin * eb, (uint64_t)g2.H * g2.W * g2.Cin * eb, p.tw, p.th);
   if (rc) return rc;
-  rc = encode_weight_map(&p.tmB, w_cat, (uint64_t)p.n_taps * g.Cin + g2.Cin, g.Cout, L->block_n);
+  L->pair = want_pair(8, L->block_n, p.n_taps * p.cblocks + p.cblocks2);
+  rc = encode_weight_map(&p.tmB, w_cat, (uint64_t)p.n_taps * g.Cin + g2.Cin, g.Cout, L->pair ? L->block_n / 2 : L->block_n);
   if (rc) return rc;
   L->out_bufs = (p.n_taps * p.cblocks + p.cblocks2 <= 8) ? 4 : 2;
+  set_grid(L);
   return 0;
 }
 
 int conv_tc_run(const ConvTcPrepared* prep, cudaStream_t stream) {
   const ConvTcLaunch* L = reinterpret_cast<const ConvTcLaunch*>(prep->storage);
   if (L->kblk == 32) return launch_bn<64, 32>(*L, stream);
+  if (L->pair) return L->block_n == 256 ? launch_pair<256>(*L, stream) : launch_pair<128>(*L, stream);
   switch (L->block_n) {
     case 256: return launch_bn<256, 64>(*L, stream);
     case 128: return launch_bn<128, 64>(*L, stream);

@@ -9,3 +9,4 @@ timeout 600 python bench.py --workload train --steps 3 --warmup 3 > gpurun_out/b
 cut -c1-300 gpurun_out/bench_train.json
 NBC_DEBUG_HANG=100 timeout 200 python bench.py --workload cli --steps 2 --warmup 1 --batch 256 > gpurun_out/bench_cli256.json 2> gpurun_out/bench_cli256.err; echo "bench cli exit $?"
 grep "^{" gpurun_out/bench_cli256.json | cut -c1-260
+timeout 200 python tools/layer_profile.py 8 624 1024 > gpurun_out/layers_final.txt 2>&1; tail -n 1 gpurun_out/layers_final.txt
