@@ -204,6 +204,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// -- programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// (barrier init, TMEM allocation, descriptor prefetch) while the previous kernel of the stream drains; pdl_wait() blocks
+// until that kernel has completed and its writes are visible.  Both are no-ops in an ordinary launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // -- CTA pair (cluster of 2, tcgen05 cta_group::2): one MMA of M = 256 spans the two SMs of a TPC -----------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -52,6 +52,9 @@ struct ConvTcParams {
   int16_t tap_dw[9];
 };
 
+#ifndef NBC_PDL_DEFAULT
+#define NBC_PDL_DEFAULT 1
+#endif
 constexpr int kRaggedHalo = 4;   // >= the largest padding / dilation of any consumer (layer4: dilation 4)
 constexpr int kTcThreads = 352;  // warp 0 TMA operands, warp 1 MMA, warps 2..9 epilogue, warp 10 output / residual TMA
 constexpr int kOutBufBytes = 128 * 64 * 2;  // 128 pixels x 64 channels x 16 bit: one output group of a tile
@@ -157,6 +160,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  // programmatic dependent launch: everything above overlapped the tail of the previous kernel; its output (our
+  // input / residual) may only be touched from here on
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
   const int kblocks = p.n_taps * p.cblocks + p.cblocks2;
@@ -468,6 +475,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int total_pairs = ((p.num_m_tiles + 1) >> 1) * p.num_n_tiles;
   const int kblocks = p.n_taps * p.cblocks + p.cblocks2;
@@ -879,6 +888,31 @@ static int build_launch(const ConvGeom& g, const void* x, const void* w, const f
   return 0;
 }
 
+// Programmatic dependent launch (environment NBC_PDL=0 switches it off): the prologue of a conv kernel -- barrier init,
+// TMEM allocation, descriptor prefetch -- runs while the previous kernel of the stream drains (see pdl_wait()).
+static bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("NBC_PDL");
+    on = (e && *e) ? (atoi(e) != 0) : NBC_PDL_DEFAULT;
+  }
+  return on != 0;
+}
+static cudaError_t launch_tc(void (*kernel)(const ConvTcParams), const ConvTcLaunch& L, int smem, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)L.grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, L.p);
+}
+
 template <int BN, int KBLK, int OB, bool RES, bool RELU, bool F16>
 static int launch_one(const ConvTcLaunch& L, cudaStream_t stream) {
   static bool attr_set = false;
@@ -887,8 +921,8 @@ static int launch_one(const ConvTcLaunch& L, cudaStream_t stream) {
                                   TcCfg<BN, KBLK, OB>::kSmemBytes));
     attr_set = true;
   }
-  conv_tc_kernel<BN, KBLK, OB, RES, RELU, F16><<<L.grid, kTcThreads, TcCfg<BN, KBLK, OB>::kSmemBytes, stream>>>(L.p);
-  NBC_CHECK_LAUNCH();
+  NBC_CUDA(launch_tc(conv_tc_kernel<BN, KBLK, OB, RES, RELU, F16>, L, TcCfg<BN, KBLK, OB>::kSmemBytes, stream));
+  count_launch();
   return 0;
 }
 
@@ -901,8 +935,8 @@ static int launch_pair_one(const ConvTcLaunch& L, cudaStream_t stream) {
     attr_set = true;
   }
   // __cluster_dims__(2, 1, 1) on the kernel: the grid is a whole number of pairs
-  conv_tc_pair_kernel<BN, OB, RES, RELU, F16><<<L.grid, kTcThreads, TcCfgPair<BN, OB>::kSmemBytes, stream>>>(L.p);
-  NBC_CHECK_LAUNCH();
+  NBC_CUDA(launch_tc(conv_tc_pair_kernel<BN, OB, RES, RELU, F16>, L, TcCfgPair<BN, OB>::kSmemBytes, stream));
+  count_launch();
   return 0;
 }
 

@@ -10,10 +10,18 @@ are its asynchronous halves: a submitted batch only enqueues work, so the host->
 under the network passes of the current one (two buffer slots) and the PCIe link -- the end-to-end bound, 50 MB per
 scan -- never idles between batches."""
 import ctypes as C
+import os
 
 import torch
 
 from . import ops
+
+
+# images per ragged batch: the per-launch cost of the 53 network kernels (launch gap, pipeline fill and drain, the last
+# partial wave) is amortised over the chunk -- 0.631 ms per image at 8, 0.608 at 12 (profiles/r01s_chunk_sweep.txt)
+DEFAULT_CHUNK = 8
+# raw-scan staging buffers of the host path (50 MB each): the H2D stream runs this many scans ahead of K1
+DEFAULT_STAGE_DEPTH = 4
 
 
 class _Slot:
@@ -39,9 +47,14 @@ class Ticket:
 
 
 class PredictEngine:
-    """chunk: images per ragged batch (one network launch sequence per chunk)."""
+    """chunk: images per ragged batch (one network launch sequence per chunk); default DEFAULT_CHUNK, or the
+    environment variable NBC_CHUNK."""
 
-    def __init__(self, model, device='cuda:0', threshold=150, raw_size=4096, chunk=8, depth=4):
+    def __init__(self, model, device='cuda:0', threshold=150, raw_size=4096, chunk=None, depth=None):
+        if chunk is None:
+            chunk = int(os.environ.get('NBC_CHUNK', DEFAULT_CHUNK))
+        if depth is None:
+            depth = int(os.environ.get('NBC_STAGE_DEPTH', DEFAULT_STAGE_DEPTH))
         self.model = model
         self.device = torch.device(device)
         self.threshold = threshold

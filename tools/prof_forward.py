@@ -24,7 +24,14 @@ m.to(dev).eval()
 m.set_normalisation(omodel.DEFAULT_MEAN, omodel.DEFAULT_STD)
 plan = m.native_plan()
 img = torch.from_numpy(synth.texture_u8(H, W, 5)).to(dev).unsqueeze(0).repeat(N, 1, 1, 1).contiguous()
+out = plan.forward(img)          # warm-up (plan creation, first-launch attributes)
+torch.cuda.synchronize()
+t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t0.record()
 for _ in range(iters):
     out = plan.forward(img)
+t1.record()
 torch.cuda.synchronize()
-print('forward x%d done, logits %s' % (iters, tuple(out.shape)))
+ms = t0.elapsed_time(t1) / iters
+print('forward x%d done, logits %s: %.3f ms per pass, %.3f ms per image (NBC_PDL=%s NBC_CTA2=%s)'
+      % (iters, tuple(out.shape), ms, ms / N, os.environ.get('NBC_PDL'), os.environ.get('NBC_CTA2')))
