@@ -779,9 +779,21 @@ static int want_pair(int cls, int bn, int kblocks) {
   if (mode >= 0) return (bn >= 128 && (mode & cls)) ? 1 : 0;
   return (bn == 256 && cls != 2 && kblocks >= 8) ? 1 : 0;
 }
+// SMs the persistent conv kernels occupy: all of them, or NBC_CONV_SMS (an experiment knob: a persistent conv CTA owns
+// its SM, so the kernels of the engine's side streams -- K1, K3, K5 -- only run between conv launches; leaving a few
+// SMs free lets them overlap the network pass at the price of that share of the conv throughput).
+static int conv_sms() {
+  static int n = -1;
+  if (n < 0) {
+    const char* e = getenv("NBC_CONV_SMS");
+    const int all = sm_count();
+    n = (e && *e && atoi(e) >= 2 && atoi(e) < all) ? (atoi(e) & ~1) : all;
+  }
+  return n;
+}
 static void set_grid(ConvTcLaunch* L) {
   const ConvTcParams& p = L->p;
-  const int sms = sm_count();
+  const int sms = conv_sms();
   if (L->pair) {
     const int pairs = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     L->grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);
