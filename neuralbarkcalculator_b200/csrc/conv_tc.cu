@@ -18,6 +18,9 @@
 //     place, so residual reads and output writes are full 128-byte lines issued by the copy engine, not by the LSU.
 // Persistent CTAs (one per SM), warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..9 = epilogue,
 // 10 = output / residual TMA.
+// Two kernels share this structure: conv_tc_kernel (one CTA per tile, cta_group::1) and conv_tc_pair_kernel (clusters
+// of 2 CTAs, one M = 256 cta_group::2 MMA over both SMs, half a weight tile per CTA -- further down); want_pair() holds
+// the measured rule that picks one per launch.  Consecutive conv launches are chained by programmatic dependent launch.
 #include <stdlib.h>
 
 #include "common.cuh"
