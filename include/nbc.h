@@ -239,6 +239,25 @@ int nbc_train_set_loss(nbc_train_plan* plan, int kind);
 int nbc_train_adam(float* params, const float* grads, float* adam_m, float* adam_v, int64_t n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 
+/* ---- result files (host side) -----------------------------------------------------------------
+ * The PNG image data of the files the hot path writes: processed/ RGB images (reference models.py:203, skimage imsave)
+ * and the 0/127/255 dual images (models.py:349-356, PIL save).  nbc_png_idat produces the complete zlib stream of ONE
+ * IDAT chunk (PNG filter Sub for 3 channels, None for 1; run-length matches + per-segment dynamic Huffman codes) from
+ * an 8-bit image in HOST memory -- chunk framing and CRC-32 are the caller's.  Pure host code: no GPU, no stream.
+ * pixels: [height][row_stride_bytes] with width*channels meaningful bytes per row (row_stride_bytes 0 = dense);
+ * lut256 (1 channel only, may be NULL): every pixel goes through this 256-entry table first -- the dual image
+ * 0/127/255 straight from the class mask (models.py:349-353).  out_cap >= nbc_png_idat_bound().
+ * Returns the number of bytes written, or a negative NBC_ERR_* status. */
+size_t nbc_png_idat_bound(int height, int width, int channels);
+int64_t nbc_png_idat(const uint8_t* pixels, int height, int width, int channels, int64_t row_stride_bytes,
+                     const uint8_t* lut256, uint8_t* out, size_t out_cap);
+/* Stand-in for the reference's two-panel figure under results/combined_images (models.py:280-347; matplotlib is not a
+ * dependency): canvas[strip_h + (height+1)/2][2*((width+1)/2) + gap][3] = the title strip the caller rendered
+ * (strip[strip_h][same width][3]) above the processed image and the class mask (colours[3 classes][3]) side by side at
+ * half resolution, `gap` white columns between them.  Host memory only. */
+int nbc_compose_combined(const uint8_t* proc_rgb, const uint8_t* mask, int height, int width, const uint8_t* colours,
+                         const uint8_t* strip, int strip_h, int gap, uint8_t* canvas);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,9 @@ SIGNATURES = {
     'nbc_confusion_matrix': (c_int, [c_void_p, c_void_p, c_int, c_i64, c_void_p, c_void_p]),
     'nbc_augment_batch': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
                           c_void_p]),
+    'nbc_png_idat_bound': (c_size_t, [c_int, c_int, c_int]),
+    'nbc_png_idat': (c_i64, [c_void_p, c_int, c_int, c_int, c_i64, c_void_p, c_void_p, c_size_t]),
+    'nbc_compose_combined': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'nbc_plan_create': (c_void_p, [C.POINTER(c_void_p), c_int, C.POINTER(c_float), C.POINTER(c_float), c_int]),
     'nbc_plan_destroy': (None, [c_void_p]),
     'nbc_plan_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int, c_int]),

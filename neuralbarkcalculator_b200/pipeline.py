@@ -33,18 +33,22 @@ _VIRIDIS3 = np.array([[68, 1, 84], [33, 145, 140], [253, 231, 37]] + [[0, 0, 0]]
 def combined_image(proc, mask, title):
     """Stand-in for the reference's two-panel matplotlib figure (models.py:280-347; matplotlib is not a dependency here):
     the processed image and the class mask in the figure's colours side by side at half resolution, the figure's
-    suptitle (class percentages) drawn in a strip above.  Same information, not the same rendering."""
+    suptitle (class percentages) drawn in a strip above.  Same information, not the same rendering.  Only the title
+    strip goes through PIL; the panels are composed by nbc_compose_combined (host code in libnbc.so, GIL released)."""
+    import ctypes as C
     from PIL import Image, ImageDraw
-    left = proc[::2, ::2]
-    right = _VIRIDIS3[mask[::2, ::2]]
-    h, w = left.shape[:2]
-    canvas = np.empty((h + 16, 2 * w + 8, 3), dtype=np.uint8)
-    canvas[16:, :w] = left
-    canvas[16:, w:w + 8] = 255
-    canvas[16:, w + 8:] = right
-    strip = Image.new('RGB', (2 * w + 8, 16), (255, 255, 255))      # only the title strip goes through PIL
+    from . import _lib
+    proc, mask = np.ascontiguousarray(proc), np.ascontiguousarray(mask)
+    h, w = mask.shape
+    hh, hw = (h + 1) // 2, (w + 1) // 2
+    strip = Image.new('RGB', (2 * hw + 8, 16), (255, 255, 255))
     ImageDraw.Draw(strip).text((4, 2), title, fill=(0, 0, 0))
-    canvas[:16] = np.asarray(strip)
+    strip = np.ascontiguousarray(np.asarray(strip))
+    canvas = np.empty((hh + 16, 2 * hw + 8, 3), dtype=np.uint8)
+    lib = _lib.load()
+    _lib.check(lib.nbc_compose_combined(C.c_void_p(proc.ctypes.data), C.c_void_p(mask.ctypes.data), h, w,
+                                        C.c_void_p(_VIRIDIS3.ctypes.data), C.c_void_p(strip.ctypes.data), 16, 8,
+                                        C.c_void_p(canvas.ctypes.data)), 'nbc_compose_combined')
     return canvas
 
 
@@ -140,7 +144,7 @@ class FolderPipeline:
             fname = fname.replace('.bmp', '.png')           # models.py:185
             write_png(join(out_proc, wood, fname), proc, self.png_level)
             if mask is not None:
-                write_png(join(out_dual, wood, fname), _DUAL_LUT[mask], self.png_level)
+                write_png(join(out_dual, wood, fname), mask, self.png_level, lut=_DUAL_LUT)
                 rows_csv[i] = [fname, wood] + self.calc._stats_strings(counts, mask.size)
                 if self.combined:
                     st = rows_csv[i]

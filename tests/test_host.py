@@ -143,6 +143,103 @@ def test_png_writer_roundtrip(tmp_path):
         _png.encode_png(img.astype(np.float32))
 
 
+def _png_idat_pixels(data, h, w, ch):
+    """Independent decoder of a PNG made by _png.encode_png: zlib inflate + undo filter 0 / 1 (numpy)."""
+    import struct
+    import zlib
+    assert data[:8] == b'\x89PNG\r\n\x1a\n'
+    pos, idat = 8, b''
+    while pos < len(data):
+        n, tag = struct.unpack('>I4s', data[pos:pos + 8])
+        body = data[pos + 8:pos + 8 + n]
+        assert struct.unpack('>I', data[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(tag + body) & 0xFFFFFFFF
+        if tag == b'IDAT':
+            idat += body
+        pos += 12 + n
+    raw = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(h, w * ch + 1)      # checks the Adler-32 too
+    out = raw[:, 1:].copy()
+    for r in range(h):
+        if raw[r, 0] == 1:
+            px = out[r].reshape(w, ch).astype(np.uint32)
+            out[r] = (np.cumsum(px, axis=0) & 0xFF).astype(np.uint8).reshape(-1)
+        else:
+            assert raw[r, 0] == 0
+    return out.reshape((h, w, ch) if ch == 3 else (h, w))
+
+
+def test_native_png_encoder(libnbc):
+    """nbc_png_idat (host code in libnbc.so: run-length + per-segment Huffman deflate) against zlib's inflate and against
+    the zlib Z_RLE encoder it replaces: same pixels for every edge case, size within 2 %."""
+    import ctypes as C
+    from neuralbarkcalculator_b200 import _png
+    from oracle import synth
+    rng = np.random.default_rng(0)
+    cases = {
+        'texture rgb': synth.texture_u8(208, 333, 3),                              # several segments (21 rows each at w=1024; here 65)
+        'texture rgb 1024 wide': synth.texture_u8(64, 1024, 5),
+        'class mask': np.array([0, 127, 255], dtype=np.uint8)[synth.class_mask(300, 512, 1)],
+        'noise rgb (stored fallback)': rng.integers(0, 256, (50, 400, 3), dtype=np.uint8),
+        'noise grey': rng.integers(0, 256, (70, 1000), dtype=np.uint8),
+        'zeros': np.zeros((100, 70), np.uint8),
+        'constant rgb': np.full((300, 300, 3), 200, np.uint8),                     # runs longer than 258 and across rows
+        '1x1 rgb': np.full((1, 1, 3), 7, np.uint8),
+        '1x1 grey': np.full((1, 1), 9, np.uint8),
+        'one column rgb': rng.integers(0, 4, (500, 1, 3), dtype=np.uint8),
+        'one row': rng.integers(0, 3, (1, 5000), dtype=np.uint8),
+        'row wider than a stored block': rng.integers(0, 2, (3, 30000, 3), dtype=np.uint8),
+        'noise row wider than a stored block': rng.integers(0, 256, (2, 70000), dtype=np.uint8),
+        'two symbols': (rng.integers(0, 2, (64, 64), dtype=np.uint8) * 255),
+        'skewed histogram (deep Huffman tree)': np.minimum(rng.geometric(0.5, (200, 320)), 255).astype(np.uint8),
+    }
+    fib = [1, 1]
+    while len(fib) < 21:
+        fib.append(fib[-1] + fib[-2])
+    deep = np.concatenate([np.full(f, k, np.uint8) for k, f in enumerate(fib)])    # Fibonacci counts: a depth-20 Huffman tree
+    cases['fibonacci histogram (code lengths must be limited to 15)'] = rng.permutation(deep).reshape(1, -1)
+    for name, a in cases.items():
+        h, w = a.shape[:2]
+        ch = 3 if a.ndim == 3 else 1
+        png = _png.encode_png(a, 1)
+        assert np.array_equal(_png_idat_pixels(png, h, w, ch), a), name
+        ref = _png.encode_png_zlib_rle(a)
+        assert np.array_equal(_png_idat_pixels(ref, h, w, ch), a), name
+        segments = -(-(h * (w * ch + 1)) // 65535) + h // max(1, 65535 // (w * ch + 1))      # ~160 header bytes each
+        assert len(png) <= len(ref) * 1.02 + 200 * (segments + 1), (name, len(png), len(ref))
+    # strided input (a window of a larger canvas), and the error paths
+    canvas = synth.texture_u8(40, 100, 2)
+    win = canvas[:, 10:60]                                                          # row stride 300 bytes, 150 meaningful
+    cap = libnbc.nbc_png_idat_bound(40, 50, 3)
+    out = np.empty(cap, dtype=np.uint8)
+    n = libnbc.nbc_png_idat(C.c_void_p(win.ctypes.data), 40, 50, 3, 300, None, C.c_void_p(out.ctypes.data), cap)
+    dense = np.empty(cap, dtype=np.uint8)
+    win_c = np.ascontiguousarray(win)
+    n2 = libnbc.nbc_png_idat(C.c_void_p(win_c.ctypes.data), 40, 50, 3, 0, None, C.c_void_p(dense.ctypes.data), cap)
+    assert n == n2 > 0 and np.array_equal(out[:n], dense[:n2])
+    assert libnbc.nbc_png_idat(C.c_void_p(win_c.ctypes.data), 40, 50, 3, 0, None, C.c_void_p(out.ctypes.data), 100) < 0
+    assert b'need' in libnbc.nbc_last_error()
+    assert libnbc.nbc_png_idat(C.c_void_p(win_c.ctypes.data), 40, 50, 2, 0, None, C.c_void_p(out.ctypes.data), cap) < 0
+    assert libnbc.nbc_png_idat_bound(0, 5, 3) == 0
+    # lookup table while encoding (dual image 0/127/255 from the class mask, models.py:349-353), file writer, compositor
+    from neuralbarkcalculator_b200 import pipeline
+    mask = synth.class_mask(123, 77, 4).astype(np.uint8)
+    for level in (0, 1, 6):
+        png = _png.encode_png(mask, level, lut=pipeline._DUAL_LUT)
+        assert np.array_equal(_png_idat_pixels(png, 123, 77, 1), pipeline._DUAL_LUT[mask])
+    lut = np.zeros(256, np.uint8)
+    assert libnbc.nbc_png_idat(C.c_void_p(win_c.ctypes.data), 40, 50, 3, 0, C.c_void_p(lut.ctypes.data), C.c_void_p(out.ctypes.data), cap) < 0
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        for a, kw in ((cases['texture rgb'], {}), (mask, {'lut': pipeline._DUAL_LUT})):
+            _png.write_png(os.path.join(d, 'a.png'), a, 1, **kw)
+            assert open(os.path.join(d, 'a.png'), 'rb').read() == _png.encode_png(a, 1, **kw)
+    proc = synth.texture_u8(123, 77, 6)
+    got = pipeline.combined_image(proc, mask, 'Bark : 12.345;  Node : 0.123   (x.png)')
+    assert got.shape == (62 + 16, 2 * 39 + 8, 3)
+    assert np.array_equal(got[16:, :39], proc[::2, ::2]) and np.all(got[16:, 39:47] == 255)
+    assert np.array_equal(got[16:, 47:], pipeline._VIRIDIS3[mask[::2, ::2]])
+    assert (got[:16] == 255).mean() > 0.5 and (got[:16] != 255).any()      # a white strip with the title drawn on it
+
+
 def test_pipeline_and_numa_host_helpers(tmp_path):
     """Host-side pieces of the folder pipeline and of the one-process-per-GPU plumbing (no GPU needed)."""
     import struct
