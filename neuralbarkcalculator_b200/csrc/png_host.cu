@@ -3,12 +3,13 @@
 //
 // Once the GPU path runs at > 1 000 scans/s the folder pipeline is bound by zlib: Z_RLE deflate of a 1.9 MB filtered
 // image takes ~27 ms per host thread.  This encoder produces the same kind of stream -- PNG filter Sub for RGB, None
-// for grey, run-length matches at distance 1, Huffman coding -- about 8x faster, because it does nothing else:
+// for grey, run-length matches at distance 1, Huffman coding -- about 5x faster, because it does nothing else:
 //   * the image is cut into segments of whole rows (<= 65 535 filtered bytes, so a segment can always fall back to ONE
 //     stored block); every segment is one deflate block with its own dynamic Huffman code, built from the segment's
 //     histogram (two passes over a cache-resident segment), runs never reach back across a segment start -- segments
 //     are therefore independent, which is what a GPU version needs (one thread block per segment);
-//   * tokens: literal bytes and (length 3..258, distance 1) matches, exactly zlib's Z_RLE vocabulary;
+//   * symbols: literal bytes and (length 3..258, distance 1) matches, exactly zlib's Z_RLE vocabulary; runs are found
+//     eight bytes at a time (SWAR zero-byte test on f[i..i+8) ^ f[i-1..i+7)), literals are appended two per store;
 //   * code lengths limited to 15 bits by rescaling the histogram (rare); the code-length alphabet uses a fixed
 //     complete code (4 bits for each of 0..15), so the block header is ~160 bytes and needs no second Huffman build.
 // The output is a complete zlib stream (header, blocks, Adler-32) = the payload of ONE IDAT chunk; chunk framing and
@@ -183,36 +184,78 @@ uint32_t adler32_update(uint32_t adler, const uint8_t* d, size_t len) {
   return (b << 16) | a;
 }
 
+struct Run {
+  int32_t pos, len;      // f[pos .. pos+len) repeats f[pos-1]: a deflate match of that length at distance 1
+};
+
+inline uint64_t load64(const uint8_t* p) {
+  uint64_t v;
+  memcpy(&v, p, 8);
+  return v;
+}
+// 0x80 in every byte of v that is zero (exact, no borrow between bytes)
+inline uint64_t zero_bytes(uint64_t v) {
+  const uint64_t k7f = 0x7F7F7F7F7F7F7F7Full;
+  return ~(((v & k7f) + k7f) | v | k7f);
+}
+
+inline void put_literals(BitWriter& bw, const uint8_t* f, int a, int b, const uint32_t* lit) {
+  int i = a;
+  for (; i + 1 < b; i += 2) {       // two literals in one append (<= 30 bits)
+    const uint32_t e0 = lit[f[i]], e1 = lit[f[i + 1]];
+    const int l0 = (int)(e0 >> 16);
+    bw.put((e0 & 0xFFFF) | ((e1 & 0xFFFF) << l0), l0 + (int)(e1 >> 16));
+  }
+  if (i < b) bw.put(lit[f[i]] & 0xFFFF, (int)(lit[f[i]] >> 16));
+}
+
 // one deflate block for the filtered bytes f[0..n), n <= kMaxSegBytes
-void encode_segment(const uint8_t* f, int n, bool final_block, BitWriter& bw_io, uint16_t* tokens) {
+void encode_segment(const uint8_t* f, int n, bool final_block, BitWriter& bw_io, Run* runs) {
   BitWriter bw = bw_io;      // a local copy lives in registers: stores through the byte pointer may alias anything else
-  // ---- pass 1: tokens + histogram.  token < 256: literal; token >= 256: run of (token - 256 + 3) copies of the
-  // previous byte (deflate match, distance 1)
+  // ---- pass 1: find the runs (>= 3 copies of the previous byte, zlib's Z_RLE vocabulary) and count the symbols.
+  // Eight bytes at a time: byte j of d is zero where f[i+j] == f[i+j-1]; three zero bytes in a row start a run.  A
+  // texture has almost none, so the common case is six literals per step without a data-dependent branch.
   uint32_t hist[4][256];
   memset(hist, 0, sizeof(hist));
   uint32_t freq[kNumLit];
   memset(freq, 0, sizeof(freq));
-  int nt = 0, matches = 0;
+  int nr = 0;
   int i = 0;
   if (n > 0) {
-    tokens[nt++] = f[0];
     hist[0][f[0]]++;
     i = 1;
   }
   while (i < n) {
-    const uint8_t prev = f[i - 1];
-    if (f[i] == prev && i + 2 < n && f[i + 1] == prev && f[i + 2] == prev) {
+    int k;      // literals before the next run start (or before the next look)
+    bool run = false;
+    if (i + 8 <= n) {
+      const uint64_t x = load64(f + i);
+      const uint64_t m = zero_bytes(x ^ load64(f + i - 1));
+      const uint64_t t = m & (m >> 8) & (m >> 16);
+      if (t == 0) {
+        hist[0][x & 0xFF]++, hist[1][(x >> 8) & 0xFF]++, hist[2][(x >> 16) & 0xFF]++;
+        hist[3][(x >> 24) & 0xFF]++, hist[0][(x >> 32) & 0xFF]++, hist[1][(x >> 40) & 0xFF]++;
+        i += 6;
+        continue;
+      }
+      k = __builtin_ctzll(t) >> 3;
+      run = true;
+    } else {
+      const uint8_t prev = f[i - 1];
+      run = f[i] == prev && i + 2 < n && f[i + 1] == prev && f[i + 2] == prev;
+      k = run ? 0 : 1;
+    }
+    for (int j = 0; j < k; ++j) hist[j & 3][f[i + j]]++;
+    i += k;
+    if (run) {
+      const uint8_t prev = f[i - 1];
       int r = 3;
       const int lim = std::min(258, n - i);
       while (r < lim && f[i + r] == prev) ++r;
-      tokens[nt++] = (uint16_t)(256 + r - 3);
+      runs[nr].pos = i, runs[nr].len = r;
+      ++nr;
       freq[kLenLut.sym[r]]++;
-      ++matches;
       i += r;
-    } else {
-      tokens[nt++] = f[i];
-      hist[i & 3][f[i]]++;
-      ++i;
     }
   }
   for (int s = 0; s < 256; ++s) freq[s] = hist[0][s] + hist[1][s] + hist[2][s] + hist[3][s];
@@ -254,36 +297,22 @@ void encode_segment(const uint8_t* f, int n, bool final_block, BitWriter& bw_io,
   for (int s = 0; s < nlit; ++s) bw.put(reverse_bits(len[s], 4), 4);
   bw.put(reverse_bits(1, 4), 4);      // the single distance code (distance 1): length 1, code '0'
 
-  // ---- pass 2: the tokens
+  // ---- pass 2: literals between the runs, the runs as (length, distance 1) matches
   uint32_t lit[256];                  // code | length << 16
   for (int s = 0; s < 256; ++s) lit[s] = code[s] | ((uint32_t)len[s] << 16);
-  tokens[nt] = 0xFFFF;               // sentinel: never a literal (the caller's buffer has room)
-  for (int t = 0; t < nt;) {
-    const uint32_t tok = tokens[t];
-    if (tok < 256) {
-      const uint32_t e0 = lit[tok];
-      const uint32_t tok1 = tokens[t + 1];
-      if (tok1 < 256) {               // two literals in one append (<= 30 bits)
-        const uint32_t e1 = lit[tok1];
-        const int l0 = (int)(e0 >> 16);
-        bw.put((e0 & 0xFFFF) | ((e1 & 0xFFFF) << l0), l0 + (int)(e1 >> 16));
-        t += 2;
-      } else {
-        bw.put(e0 & 0xFFFF, (int)(e0 >> 16));
-        ++t;
-      }
-    } else {
-      const int L = (int)tok - 256 + 3;
-      const int sym = kLenLut.sym[L];
-      bw.put(code[sym], len[sym]);
-      if (kLenLut.extra_bits[L]) bw.put(kLenLut.extra_val[L], kLenLut.extra_bits[L]);
-      bw.put(0, 1);                   // distance code 0 = distance 1, no extra bits
-      ++t;
-    }
+  int pos = 0;
+  for (int r = 0; r < nr; ++r) {
+    put_literals(bw, f, pos, runs[r].pos, lit);
+    const int L = runs[r].len;
+    const int sym = kLenLut.sym[L];
+    bw.put(code[sym], len[sym]);
+    if (kLenLut.extra_bits[L]) bw.put(kLenLut.extra_val[L], kLenLut.extra_bits[L]);
+    bw.put(0, 1);                     // distance code 0 = distance 1, no extra bits
+    pos = runs[r].pos + L;
   }
+  put_literals(bw, f, pos, n, lit);
   bw.put(code[256], len[256]);
   bw_io = bw;
-  (void)matches;
 }
 
 }  // namespace
@@ -329,7 +358,7 @@ extern "C" int64_t nbc_png_idat(const uint8_t* pixels, int height, int width, in
 
   const int rows_per_seg = (int)std::max<int64_t>(1, kMaxSegBytes / frow);
   std::vector<uint8_t> seg((size_t)std::max<int64_t>(frow, (int64_t)rows_per_seg * frow));
-  std::vector<uint16_t> tokens((size_t)kMaxSegBytes + 8);
+  std::vector<Run> runs((size_t)kMaxSegBytes / 3 + 8);
   const bool sub = channels == 3 && width > 1;      // filter 1 (Sub) for RGB, 0 (None) for grey masks
   for (int r0 = 0; r0 < height; r0 += rows_per_seg) {
     const int nr = std::min(rows_per_seg, height - r0);
@@ -354,7 +383,7 @@ extern "C" int64_t nbc_png_idat(const uint8_t* pixels, int height, int width, in
     // a row wider than 65 535 bytes is cut into several blocks
     for (int64_t o = 0; o < nbytes; o += kMaxSegBytes) {
       const int n = (int)std::min<int64_t>(kMaxSegBytes, nbytes - o);
-      encode_segment(seg.data() + o, n, last_seg && o + n >= nbytes, bw, tokens.data());
+      encode_segment(seg.data() + o, n, last_seg && o + n >= nbytes, bw, runs.data());
     }
   }
   bw.align_byte();
