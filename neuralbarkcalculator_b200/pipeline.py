@@ -30,20 +30,50 @@ _DUAL_LUT = np.array([0, 127, 255] + [0] * 253, dtype=np.uint8)     # models.py:
 _VIRIDIS3 = np.array([[68, 1, 84], [33, 145, 140], [253, 231, 37]] + [[0, 0, 0]] * 253, dtype=np.uint8)
 
 
+_GLYPHS = {}       # character -> (uint8 [16, advance] grey glyph on white, advance in pixels): rendered by PIL once
+
+
+def _glyph(ch):
+    g = _GLYPHS.get(ch)
+    if g is None:
+        from PIL import Image, ImageDraw, ImageFont
+        font = _GLYPHS.get('font')
+        if font is None:
+            font = _GLYPHS['font'] = ImageFont.load_default()
+        adv = max(1, int(np.ceil(font.getlength(ch)))) if hasattr(font, 'getlength') else 6
+        im = Image.new('L', (adv + 2, 16), 255)
+        ImageDraw.Draw(im).text((0, 2), ch, fill=0, font=font)
+        g = _GLYPHS[ch] = (np.ascontiguousarray(np.asarray(im)), adv)
+    return g
+
+
+def title_strip(title, width, height=16):
+    """White RGB strip [height, width, 3] with the title in black.  Glyphs come from PIL's default font, rendered once
+    per character and cached -- a full PIL text render per image holds the GIL for 1.5 ms and would cap the writer
+    threads at ~600 images/s."""
+    strip = np.full((height, width), 255, dtype=np.uint8)
+    x = 4
+    for ch in title:
+        g, adv = _glyph(ch)
+        w = min(g.shape[1], width - x)
+        if w <= 0:
+            break
+        np.minimum(strip[:, x:x + w], g[:height, :w], out=strip[:, x:x + w])
+        x += adv
+    return np.repeat(strip[:, :, None], 3, axis=2)
+
+
 def combined_image(proc, mask, title):
     """Stand-in for the reference's two-panel matplotlib figure (models.py:280-347; matplotlib is not a dependency here):
     the processed image and the class mask in the figure's colours side by side at half resolution, the figure's
-    suptitle (class percentages) drawn in a strip above.  Same information, not the same rendering.  Only the title
-    strip goes through PIL; the panels are composed by nbc_compose_combined (host code in libnbc.so, GIL released)."""
+    suptitle (class percentages) drawn in a strip above.  Same information, not the same rendering.  The panels are
+    composed by nbc_compose_combined (host code in libnbc.so, GIL released)."""
     import ctypes as C
-    from PIL import Image, ImageDraw
     from . import _lib
     proc, mask = np.ascontiguousarray(proc), np.ascontiguousarray(mask)
     h, w = mask.shape
     hh, hw = (h + 1) // 2, (w + 1) // 2
-    strip = Image.new('RGB', (2 * hw + 8, 16), (255, 255, 255))
-    ImageDraw.Draw(strip).text((4, 2), title, fill=(0, 0, 0))
-    strip = np.ascontiguousarray(np.asarray(strip))
+    strip = title_strip(title, 2 * hw + 8)
     canvas = np.empty((hh + 16, 2 * hw + 8, 3), dtype=np.uint8)
     lib = _lib.load()
     _lib.check(lib.nbc_compose_combined(C.c_void_p(proc.ctypes.data), C.c_void_p(mask.ctypes.data), h, w,
