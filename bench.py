@@ -47,6 +47,8 @@ def parse():
     ap.add_argument('--batch', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp16'],
+                    help='16-bit storage format of activations / weights on the predict path (same tcgen05 kind::f16 rate)')
     return ap.parse_args()
 
 
@@ -210,7 +212,7 @@ def main():
     # one process per GPU: keep this rank's pinned staging buffers on the NUMA node of its GPU (see bind_to_gpu_numa)
     numa = ndist.bind_to_gpu_numa(local_rank) if world > 1 else {'numa_node': ndist.gpu_numa_node(local_rank), 'bound': False}
 
-    calc = nbc.NeuralBarkCalculator(None, str(dev), state_dict=sd)
+    calc = nbc.NeuralBarkCalculator(None, str(dev), state_dict=sd, precision=args.precision)
     eng = engine.PredictEngine(calc.model, dev)
     hbm_peak, tf_peak, peak_kind = peaks()
 
@@ -441,7 +443,7 @@ def main():
     if rank == 0:
         line = {'metric': 'images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-                'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+                'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
                 'config': {'workload': workload, 'images_per_step_per_gpu': n_img, 'parallelism': 'dp%d (images sharded, no collective)' % world,
                            'numa': numa,
                            'l2': 'inputs (%.1f GB per rank) larger than L2; no flush needed' % (n_img * RAW * RAW * 3 / 1e9)},
