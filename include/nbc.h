@@ -53,6 +53,15 @@ int64_t nbc_launch_count(void);
 size_t nbc_preprocess_workspace_bytes(int H, int W);
 int nbc_preprocess_4x_u8(const uint8_t* raw, int H, int W, int64_t pitch, int flags, uint8_t* out,
                          int32_t* first_last, void* workspace, size_t workspace_bytes, void* stream);
+/* General ratio: any H x W image whose larger side exceeds `target` becomes target x target (models.py:194-198,
+ * skimage resize order 3, mode 'reflect', no anti-aliasing, clipped to the input range), then trim_black and the
+ * float -> u8 rounding -- float64 arithmetic in the order of oracle/preprocess.py::resize_general_f64.  Same flags,
+ * outputs and conventions as nbc_preprocess_4x_u8; out capacity target*target*3.
+ * EXPERIMENTAL in round 1: built and compiled, not yet run on a GPU (the Python mirror only routes to it when
+ * NBC_GENERAL_RESIZE=1; otherwise non-4x sizes are rejected loudly). */
+size_t nbc_preprocess_general_workspace_bytes(int H, int W, int target);
+int nbc_preprocess_general_u8(const uint8_t* raw, int H, int W, int64_t pitch, int flags, int target, uint8_t* out,
+                              int32_t* first_last, void* workspace, size_t workspace_bytes, void* stream);
 /* trim only, for images that need no resize (max dim <= 1024, models.py:194,200) */
 int nbc_trim_u8(const uint8_t* img, int H, int W, uint8_t* out, int32_t* first_last, void* workspace,
                 size_t workspace_bytes, void* stream);

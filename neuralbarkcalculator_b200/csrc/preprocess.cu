@@ -238,6 +238,100 @@ __global__ void __launch_bounds__(256) copy_rows_u8(const uint8_t* __restrict__ 
 
 static size_t pre_header_bytes(int Ho) { return align_up(sizeof(PreHeader) + (size_t)Ho * sizeof(int), 256); }
 
+// ------------------------------------------------------------------------------------------------------------
+// General-ratio resize: any H x W image whose larger side exceeds the target becomes target x target
+// (models.py:194-198: skimage.transform.resize(image, (1024, 1024), order=3, mode='reflect', anti_aliasing=False)).
+// Restated as in oracle/preprocess.py::resize_general_f64 -- float64, separable Catmull-Rom cubic convolution
+// (columns first, then rows), source coordinate (dst + 0.5) * (n_in / n_out) - 0.5, taps floor(src) - 1 .. + 2 reflected
+// symmetrically at the border, result clipped to the input's global [min, max], u8 = floor(v + 0.5), non-dark iff
+// (v0/255 + v1/255) + v2/255 > 1e-3 -- with every operation written as an explicitly rounded f64 intrinsic in the
+// oracle's order (no FMA contraction), so that the bytes match the restatement.  Not a bandwidth kernel: one thread per
+// output pixel gathers 4 x 4 x 3 input bytes; the 4x path above stays the one for the scanner's 4096^2 images.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) minmax_u8(const uint8_t* __restrict__ raw, int H, int W, int64_t pitch, PreHeader* hdr) {
+  int mn = 255, mx = 0;
+  const int64_t rowb = (int64_t)W * 3;
+  for (int r = blockIdx.x; r < H; r += gridDim.x) {
+    const uint8_t* p = raw + (int64_t)r * pitch;
+    for (int64_t i = threadIdx.x; i < rowb; i += blockDim.x) {
+      const int v = p[i];
+      mn = min(mn, v), mx = max(mx, v);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&hdr->inv_min, 255 - mn);
+    atomicMax(&hdr->max, mx);
+  }
+}
+
+struct CubicTaps {
+  int idx[4];
+  double t;
+};
+__device__ __forceinline__ CubicTaps cubic_taps(int n_in, int n_out, int o) {
+  CubicTaps c;
+  const double scale = __ddiv_rn((double)n_in, (double)n_out);
+  const double src = __dsub_rn(__dmul_rn(__dadd_rn((double)o, 0.5), scale), 0.5);
+  const double fl = floor(src);
+  c.t = __dsub_rn(src, fl);
+  const int i0 = (int)fl;
+  const int period = 2 * n_in;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int id = (i0 + k - 1) % period;
+    if (id < 0) id += period;
+    c.idx[k] = id >= n_in ? period - 1 - id : id;      // numpy 'symmetric': d c b a | a b c d | d c b a
+  }
+  return c;
+}
+// f1 + 0.5 x (f2 - f0 + x (2 f0 - 5 f1 + 4 f2 - f3 + x (3 (f1 - f2) + f3 - f0))), evaluated left to right as numpy does
+__device__ __forceinline__ double cubic_f64(double f0, double f1, double f2, double f3, double x) {
+  const double a = __dsub_rn(__dadd_rn(__dmul_rn(3.0, __dsub_rn(f1, f2)), f3), f0);
+  const double b = __dadd_rn(
+      __dsub_rn(__dadd_rn(__dsub_rn(__dmul_rn(2.0, f0), __dmul_rn(5.0, f1)), __dmul_rn(4.0, f2)), f3), __dmul_rn(x, a));
+  const double c = __dadd_rn(__dsub_rn(f2, f0), __dmul_rn(x, b));
+  return __dadd_rn(f1, __dmul_rn(__dmul_rn(0.5, x), c));
+}
+
+__global__ void __launch_bounds__(256) resize_general_kernel(const uint8_t* __restrict__ raw, int H, int W, int64_t pitch,
+                                                             int flags, int Ho, int Wo, const PreHeader* __restrict__ hdr,
+                                                             uint8_t* __restrict__ r8, int* __restrict__ rowcount) {
+  const int ho = blockIdx.y;
+  const int wo = blockIdx.x * blockDim.x + threadIdx.x;
+  int nondark = 0;
+  if (wo < Wo) {
+    const CubicTaps rt = cubic_taps(H, Ho, ho), ct = cubic_taps(W, Wo, wo);
+    const double lo = (double)(255 - hdr->inv_min), hi = (double)hdr->max;
+    double v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int cs = (flags & 1) ? 2 - c : c;      // BGR source
+      double col[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = rt.idx[k];
+        const uint8_t* p = raw + ((flags & 2) ? (int64_t)(H - 1 - r) : (int64_t)r) * pitch + cs;
+        col[k] = cubic_f64((double)p[(int64_t)ct.idx[0] * 3], (double)p[(int64_t)ct.idx[1] * 3], (double)p[(int64_t)ct.idx[2] * 3],
+                           (double)p[(int64_t)ct.idx[3] * 3], ct.t);
+      }
+      double o = cubic_f64(col[0], col[1], col[2], col[3], rt.t);
+      o = fmin(fmax(o, lo), hi);      // np.clip(out, img.min(), img.max())
+      v[c] = o;
+      r8[((int64_t)ho * Wo + wo) * 3 + c] = (uint8_t)(int)floor(__dadd_rn(o, 0.5));
+    }
+    const double s = __dadd_rn(__dadd_rn(__ddiv_rn(v[0], 255.0), __ddiv_rn(v[1], 255.0)), __ddiv_rn(v[2], 255.0));
+    nondark = s > 1e-3 ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nondark += __shfl_xor_sync(0xffffffffu, nondark, o);
+  if ((threadIdx.x & 31) == 0 && nondark) atomicAdd(&rowcount[ho], nondark);
+}
+
 }  // namespace nbc
 
 using namespace nbc;
@@ -297,6 +391,41 @@ extern "C" int nbc_trim_u8(const uint8_t* img, int H, int W, uint8_t* out, int32
   trim_rows_kernel<<<1, 1024, 0, stream>>>(rowcount, nullptr, H, W, H == W ? 1 : 0, first_last);
   NBC_CHECK_LAUNCH();
   copy_rows_u8<<<4 * 148, 256, 0, stream>>>(img, W, first_last, out);
+  NBC_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" size_t nbc_preprocess_general_workspace_bytes(int H, int W, int target) {
+  (void)H, (void)W;
+  if (target <= 0) return 0;
+  return pre_header_bytes(target) + align_up((size_t)target * target * 3, 256);
+}
+
+extern "C" int nbc_preprocess_general_u8(const uint8_t* raw, int H, int W, int64_t pitch, int flags, int target, uint8_t* out,
+                                         int32_t* first_last, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  NBC_REQUIRE(raw && out && first_last && workspace, "nbc_preprocess_general_u8: null pointer");
+  NBC_REQUIRE(H > 0 && W > 0 && target > 0 && H < (1 << 20) && W < (1 << 20), "nbc_preprocess_general_u8: bad shape %dx%d -> %d", H, W,
+              target);
+  NBC_REQUIRE(pitch >= (int64_t)W * 3, "nbc_preprocess_general_u8: pitch %lld < 3*W", (long long)pitch);
+  if (workspace_bytes < nbc_preprocess_general_workspace_bytes(H, W, target)) {
+    set_error("nbc_preprocess_general_u8: workspace %zu < %zu", workspace_bytes, nbc_preprocess_general_workspace_bytes(H, W, target));
+    return NBC_ERR_WORKSPACE;
+  }
+  const int Ho = target, Wo = target;
+  char* ws = reinterpret_cast<char*>(workspace);
+  PreHeader* hdr = reinterpret_cast<PreHeader*>(ws);
+  int* rowcount = reinterpret_cast<int*>(ws + sizeof(PreHeader));
+  uint8_t* r8 = reinterpret_cast<uint8_t*>(ws + pre_header_bytes(target));
+  NBC_CUDA(cudaMemsetAsync(ws, 0, sizeof(PreHeader) + (size_t)Ho * sizeof(int), stream));
+  minmax_u8<<<H < 4 * 148 ? H : 4 * 148, 256, 0, stream>>>(raw, H, W, pitch, hdr);
+  NBC_CHECK_LAUNCH();
+  resize_general_kernel<<<dim3(ceil_div(Wo, 256), Ho), 256, 0, stream>>>(raw, H, W, pitch, flags, Ho, Wo, hdr, r8, rowcount);
+  NBC_CHECK_LAUNCH();
+  // the resized image is target x target, i.e. square: trim_black always applies (models.py:200)
+  trim_rows_kernel<<<1, 1024, 0, stream>>>(rowcount, hdr, Ho, Wo, 1, first_last);
+  NBC_CHECK_LAUNCH();
+  copy_rows_u8<<<4 * 148, 256, 0, stream>>>(r8, Wo, first_last, out);
   NBC_CHECK_LAUNCH();
   return 0;
 }

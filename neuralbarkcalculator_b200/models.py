@@ -144,8 +144,16 @@ class Preprocessor():
         raw = t.pin_memory().to(self.device, non_blocking=True) if t.numel() > (1 << 20) else t.to(self.device)
         if max(H, W) > self.target_size:
             if H != 4 * self.target_size or W != 4 * self.target_size:
+                if os.environ.get('NBC_GENERAL_RESIZE', '0') == '1':
+                    # general-ratio kernel (f64 restatement of skimage's order-3 resize): built in round 1 but not yet
+                    # verified on a GPU, hence opt-in
+                    out, fl = ops.preprocess_general(raw, H, W, self.target_size, pitch, bgr=bgr, bottom_up=bottom_up)
+                    first, last = fl.tolist()
+                    T = self.target_size
+                    return out[:(last - first) * T * 3].view(last - first, T, 3)
                 raise NotImplementedError(
-                    'only the 4x reduction %dx%d -> %dx%d is built (got %dx%d); no fallback resize'
+                    'only the 4x reduction %dx%d -> %dx%d is enabled (got %dx%d); no fallback resize '
+                    '(NBC_GENERAL_RESIZE=1 opts into the experimental general-ratio kernel)'
                     % (4 * self.target_size, 4 * self.target_size, self.target_size, self.target_size, H, W))
             out, fl = ops.preprocess_4x(raw, H, W, pitch, bgr=bgr, bottom_up=bottom_up)
             first, last = fl.tolist()

@@ -60,6 +60,23 @@ def preprocess_4x(raw, H, W, pitch=None, bgr=False, bottom_up=False, workspace=N
     return out, fl
 
 
+def preprocess_general(raw, H, W, target=1024, pitch=None, bgr=False, bottom_up=False):
+    """General-ratio variant of ``preprocess_4x``: any H x W pixel array -> target x target cubic resize + trim
+    (models.py:194-203).  Returns (out u8 [target*target*3] flat buffer, first_last int32[2] CUDA tensor); the trimmed
+    image is ``out[:(last-first)*target*3].view(last-first, target, 3)``.  EXPERIMENTAL (see include/nbc.h)."""
+    lib = _lib.load()
+    raw = _contig(raw, torch.uint8, 'raw')
+    pitch = W * 3 if pitch is None else pitch
+    with torch.cuda.device(raw.device):
+        ws = torch.empty(lib.nbc_preprocess_general_workspace_bytes(H, W, target), dtype=torch.uint8, device=raw.device)
+        out = torch.empty(target * target * 3, dtype=torch.uint8, device=raw.device)
+        fl = torch.empty(2, dtype=torch.int32, device=raw.device)
+        _lib.check(lib.nbc_preprocess_general_u8(_ptr(raw), H, W, pitch, (1 if bgr else 0) | (2 if bottom_up else 0), target,
+                                                 _ptr(out), _ptr(fl), _ptr(ws), ws.numel(), _stream(raw.device)),
+                   'nbc_preprocess_general_u8')
+    return out, fl
+
+
 def trim_u8(img):
     """img: u8 CUDA [H, W, 3] that needs no resize -> (out flat, first_last).  (models.py:157-166, 200-201)"""
     lib = _lib.load()

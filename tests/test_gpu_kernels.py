@@ -82,6 +82,37 @@ def test_preprocess_full_size_and_edges(cuda_device):
     assert (first, last) == (0, 16) and np.array_equal(out, expect)
 
 
+@pytest.mark.skipif(os.environ.get('NBC_TEST_EXPERIMENTAL', '0') != '1',
+                    reason='general-ratio resize kernel: built in round 1, not yet verified on a GPU (NBC_TEST_EXPERIMENTAL=1 runs it)')
+def test_preprocess_general_ratio(cuda_device):
+    """Any size -> target x target (models.py:194-198) against the f64 restatement, byte for byte: non-integer ratios both
+    ways, upscaling of one axis, BGR / bottom-up sources, dark bands that trigger the trim, an input range that clips."""
+    ops = _ops()
+    for (H, W, target, seed, bgr, bottom_up) in [(300, 500, 128, 1, False, False), (517, 333, 200, 2, True, True),
+                                                 (1000, 90, 96, 3, True, False), (130, 129, 128, 4, False, True)]:
+        raw = synth.texture_u8(H, W, seed)
+        raw[:H // 6] = 0
+        raw[H - H // 9:] = 0
+        raw = np.clip(raw, 0, 230).astype(np.uint8)
+        exp, f, l = opre.preprocess_u8(raw, target)
+        src = raw[..., ::-1] if bgr else raw
+        src = src[::-1] if bottom_up else src
+        t = torch.from_numpy(np.ascontiguousarray(src)).to(cuda_device)
+        out, fl = ops.preprocess_general(t.view(-1), H, W, target, bgr=bgr, bottom_up=bottom_up)
+        first, last = fl.tolist()
+        got = out[:(last - first) * target * 3].view(last - first, target, 3).cpu().numpy()
+        assert (first, last) == (f, l), (H, W, target)
+        assert np.array_equal(got, exp), (H, W, target, int((got != exp).sum()))
+    # at the exact 4x ratio the f64 path agrees with the integer kernel except on exact .5 ties
+    raw = synth.texture_u8(512, 512, 7)
+    t = torch.from_numpy(raw).to(cuda_device)
+    a, fla = ops.preprocess_general(t.view(-1), 512, 512, 128)
+    b, flb = ops.preprocess_4x(t.view(-1), 512, 512)
+    assert fla.tolist() == flb.tolist()
+    d = (a.cpu().numpy().astype(np.int16) - b.cpu().numpy().astype(np.int16))
+    assert np.abs(d).max() <= 1 and (d != 0).mean() < 0.01
+
+
 def test_trim_u8(cuda_device):
     ops = _ops()
     img = synth.texture_u8(96, 96, 4)
