@@ -266,3 +266,18 @@ def test_pipeline_and_numa_host_helpers(tmp_path):
     p = augment.draw_params(np.random.default_rng(0), 64, 5, 512)
     assert p['x0'].max() <= 512 and p['y0'].min() >= 0 and set(np.unique(p['order'])) <= {0, 1} and p['src'].max() < 5
     assert 0.9 <= p['brightness'].min() and p['brightness'].max() <= 1.1 and 0.8 <= p['saturation'].min() and p['saturation'].max() <= 1.2
+
+
+def test_profile_tools_read_the_committed_launch_list():
+    """tools/kernel_shares.py on the committed ncu launch list: the timed step of the bench is 176 launches, 100 of them
+    tensor-core convolutions (49 per chunk of 8 scans + the stem), and the shares add up."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csv_path = os.path.join(root, 'profiles', 'r01u_launches_bench_batch16.csv')
+    out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'kernel_shares.py'), csv_path, '176', '--from', '475'],
+                         capture_output=True, text=True, check=True).stdout
+    rows = {l.split()[0]: l.split() for l in out.splitlines() if 'launches' in l and not l.startswith('total')}
+    assert int(rows['conv_tc_pair_kernel'][1]) + int(rows['conv_tc_kernel'][1]) == 100
+    assert abs(sum(float(r[-2]) for r in rows.values()) - 100.0) < 0.5
+    assert 'total' in out and '176 launches' in out
