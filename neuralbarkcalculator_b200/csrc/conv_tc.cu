@@ -844,7 +844,14 @@ static int build_launch(const ConvGeom& g, const void* x, const void* w, const f
   choose_tile(Ho, Wo, &p);
   p.N = g.N, p.Ho = Ho, p.Wo = Wo, p.Cout = g.Cout;
   p.num_m_tiles = g.N * p.tiles_w * p.tiles_h;
-  const int bn = (g.Cout % 256 == 0) ? 256 : (g.Cout % 128 == 0 ? 128 : 64);
+  int bn = (g.Cout % 256 == 0) ? 256 : (g.Cout % 128 == 0 ? 128 : 64);
+  // experiment knob: 128-column tiles on the residual layers (32 KB operand stages: 5 of them next to the 4 staging
+  // buffers instead of 3 -- ncu shows those launches at ~50 % of DRAM, L2 and tensor pipe alike, i.e. latency bound)
+  static const int res_bn = [] {
+    const char* e = getenv("NBC_RES_BN");
+    return (e && *e) ? atoi(e) : 0;
+  }();
+  if (residual != nullptr && res_bn == 128 && g.Cout % 128 == 0) bn = 128;
   L->block_n = bn;
   L->kblk = 64;
   p.num_n_tiles = g.Cout / bn;

@@ -23,3 +23,5 @@ PROF="python tools/prof_forward.py 8 624 1024 3"
 timeout 700 ncu --set full --clock-control none --import-source on -k regex:conv_tc_ -s 98 -c 49 -o /tmp/conv_full $PROF > gpurun_out/ncu_full.log 2>&1; echo "ncu full exit $?"
 ncu -i /tmp/conv_full.ncu-rep --page raw --csv > gpurun_out/conv_full_raw.csv 2>/dev/null
 python tools/ncu_summarise.py gpurun_out/conv_full_raw.csv gpurun_out/ncu_conv_tc_full.txt gpurun_out/ncu_traffic.json
+# (5) residual 1x1 expansions on 128-column tiles (5 operand stages instead of 3)
+for v in 0 128; do NBC_RES_BN=$v timeout 200 python tools/layer_profile.py 8 624 1024 > gpurun_out/layers_resbn$v.txt 2>&1; echo "NBC_RES_BN=$v"; tail -n 1 gpurun_out/layers_resbn$v.txt; done
