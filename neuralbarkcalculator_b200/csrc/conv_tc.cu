@@ -53,6 +53,9 @@ struct ConvTcParams {
   int8_t tap_map[9];
   int16_t tap_dh[9];
   int16_t tap_dw[9];
+  // stem only (conv_tc_stem_kernel): the zero-padded staging image [N][stem_hp][stem_wp][4] (see stem.cu)
+  const uint8_t* stem_src;
+  int stem_hp, stem_wp;
 };
 
 #ifndef NBC_PDL_DEFAULT
@@ -691,6 +694,226 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Stem variant with a HALO tile (EXPERIMENTAL, NBC_STEM_HALO=1; not yet run on a GPU).  conv_tc_kernel<64, 32> fetches
+// the stem's A operand as 7 boxes of 128 rows x 64 bytes per tile -- 896 L2 requests of 1.4 sectors each, and ncu shows
+// the launch bound by that request rate (12 % tensor-pipe activity).  The windows of neighbouring outputs overlap: tap
+// row ky of output wo is the 64 bytes (8 pixels x 4 channels) at padded pixel 2*wo, i.e. 16 bytes after the window of
+// output wo - 1.  16 bytes is exactly the row pitch of a NO-SWIZZLE K-major UMMA core matrix (8 rows x 16 bytes, rows
+// 16 bytes apart): with LBO = 16 B (next 16 bytes of K) and SBO = 128 B (next 8 rows) a descriptor reads the 128
+// overlapping windows of a tile straight out of one contiguous input row.  So a 128 x 1 output tile needs 7 bulk copies
+// of 2 096 bytes (one per tap row) instead of 896 small requests, and the 28 KB of stem weights stay resident in
+// shared memory for the whole kernel.  Epilogue / output path as in conv_tc_kernel<64, ...>.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kStemRowBytes = 2112;                 // (2 * 127 + 8) pixels x 8 B = 2 096, rounded up to a multiple of 64
+constexpr int kStemStageBytes = 7 * kStemRowBytes + 64;      // 14 848 = 116 x 128
+constexpr int kStemStages = 6;
+constexpr int kStemOB = 4;
+constexpr int kStemWBytes = 7 * 64 * 64;            // 7 tap rows x 64 output channels x 32 k (64B-swizzled boxes)
+constexpr int kStemSmemBytes = kStemStages * kStemStageBytes + kStemWBytes + kStemOB * kOutBufBytes + 256 + 1024;
+static_assert(kStemSmemBytes <= kSmemLimit && kStemSmemBytes > 120 * 1024, "stem halo kernel: shared memory budget");
+static_assert(kStemStageBytes % 128 == 0 && (kStemStages * kStemStageBytes) % 1024 == 0, "stem halo kernel: alignment");
+
+__device__ __forceinline__ void bulk_load_1d(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem)),
+               "l"(reinterpret_cast<uint64_t>(gmem)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// K-major operand WITHOUT swizzle: 8-row x 16-byte core matrices, rows 16 bytes apart (fixed by the hardware),
+// LBO = distance between the two 16-byte K halves of one MMA, SBO = distance between 8-row groups
+__device__ __forceinline__ uint64_t umma_desc_kmajor_noswizzle(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;      // layout type 0 = no swizzle
+}
+
+template <bool RELU, bool F16>
+__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_stem_kernel(const __grid_constant__ ConvTcParams p) {
+  constexpr int BN = 64, OB = kStemOB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wres = smem + kStemStages * kStemStageBytes;      // resident weights, 1024-aligned
+  uint8_t* obuf = wres + kStemWBytes;                        // OB staging buffers, 1024-aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(obuf + OB * kOutBufBytes);
+  uint64_t* empty_bar = full_bar + kStemStages;
+  uint64_t* tfull_bar = empty_bar + kStemStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* bufready_bar = tempty_bar + 2;
+  uint64_t* outready_bar = bufready_bar + OB;
+  uint64_t* w_bar = outready_bar + OB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStemStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);
+    }
+    for (int i = 0; i < OB; ++i) {
+      mbar_init(&bufready_bar[i], 1);
+      mbar_init(&outready_bar[i], 8);
+    }
+    mbar_init(w_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&p.tmB);
+  if (warp == 10 && lane == 0) tma_prefetch_desc(&p.tmOut);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  pdl_launch_dependents();
+  pdl_wait();
+
+  const int total_tiles = p.num_m_tiles;      // one N tile: all 64 output channels
+
+  if (warp == 0) {
+    // ================================ producer: weights once, then 7 input rows per tile ================================
+    if (elect_one()) {
+      mbar_expect_tx(w_bar, kStemWBytes);
+      for (int ky = 0; ky < 7; ++ky) tma_load_2d(wres + ky * 4096, &p.tmB, w_bar, ky * 32, 0);
+      uint32_t stage = 0, phase = 0;
+      const int64_t row_bytes = (int64_t)p.stem_wp * 8;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        if (tile_dead(p, tile)) continue;
+        const TileCoord t = tile_coord(p, tile);      // tw = 128, th = 1: h0 = output row, w0 = first output column
+        // what is left of the padded row from pixel 2 * w0 on (a multiple of 16 bytes); beyond it lie outputs >= Wo
+        const uint32_t len = (uint32_t)min((int64_t)(2 * 127 + 8) * 8, row_bytes - (int64_t)t.w0 * 16);
+        mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + (int)stage);
+        uint8_t* sA = smem + stage * kStemStageBytes;
+        mbar_expect_tx(&full_bar[stage], 7 * len);
+        const uint8_t* src = p.stem_src + ((int64_t)t.img * p.stem_hp + 2 * t.h0) * row_bytes + (int64_t)t.w0 * 16;
+        for (int ky = 0; ky < 7; ++ky) bulk_load_1d(sA + ky * kStemRowBytes, src + ky * row_bytes, len, &full_bar[stage]);
+        if (++stage == kStemStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (elect_one()) {
+      constexpr uint32_t idesc = F16 ? umma_idesc_f16(128, BN) : umma_idesc_bf16(128, BN);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      mbar_wait(w_bar, 0, 700);
+      const uint32_t w_addr = smem_u32(wres);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        if (tile_dead(p, tile)) continue;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 300 + (int)acc);
+        mbar_wait(&full_bar[stage], phase, 200 + (int)stage);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t a_addr = smem_u32(smem + stage * kStemStageBytes);
+#pragma unroll
+        for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {      // K = 32 per tap row = two MMAs of K = 16 (32 bytes)
+            umma_bf16(d_tmem, umma_desc_kmajor_noswizzle(a_addr + ky * kStemRowBytes + k * 32, 16, 128),
+                      umma_desc_kmajor<64>(w_addr + ky * 4096 + k * 32), idesc, (uint32_t)((ky | k) != 0));
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&tfull_bar[acc]);
+        if (++stage == kStemStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 10) {
+    // ================================ output TMA ================================
+    if (elect_one()) {
+      uint32_t st_s = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        if (tile_dead(p, tile)) continue;
+        const uint32_t b = st_s % OB;
+        mbar_wait(&outready_bar[b], (st_s / OB) & 1u, 500 + (int)b);
+        const TileCoord t = tile_coord(p, tile);
+        tma_store_4d(&p.tmOut, obuf + b * kOutBufBytes, 0, t.w0, t.h0, t.img);
+        tma_store_commit();
+        tma_store_wait_read<0>();
+        mbar_arrive(&bufready_bar[b]);
+        ++st_s;
+      }
+      tma_store_wait_all();
+    }
+    __syncwarp();
+  } else {
+    // ================================ epilogue (warps 2..9): as conv_tc_kernel with BN = 64 ================================
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;            // which 32 of the 64 columns
+    const int row = q * 32 + lane;
+    const uint32_t row_off = (uint32_t)row * 128u;
+    const uint32_t rsw = (uint32_t)(row & 7);
+    const int u0 = half * 4;
+    uint32_t acc = 0, acc_phase = 0, live_tiles = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = tile_coord(p, tile);
+      const int vh = p.valid_h != nullptr ? __ldg(p.valid_h + t.img) : INT_MAX;
+      const int h = t.h0, w = t.w0 + row;
+      if (t.h0 >= vh) {
+        if (t.h0 < vh + kRaggedHalo && w < p.Wo && h < p.Ho) {
+          __nv_bfloat16* o = p.out + (((int64_t)t.img * p.Ho + h) * p.Wo + w) * p.Cout + half * 32;
+          for (int c = 0; c < 32; c += 8) *reinterpret_cast<uint4*>(o + c) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        continue;
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase, 400 + (int)acc);
+      tc_fence_after();
+      const uint32_t s = live_tiles;
+      const uint32_t b = s % OB;
+      uint32_t a[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + u0 * 8, a);
+      const float* bptr = p.bias + u0 * 8;
+      mbar_wait(&bufready_bar[b], ((s / OB) & 1u) ^ 1u, 600 + (int)b);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      uint8_t* rowp = obuf + b * kOutBufBytes + row_off;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bptr + u * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bptr + u * 8 + 4));
+        float v[8] = {__uint_as_float(a[u * 8 + 0]) + b0.x, __uint_as_float(a[u * 8 + 1]) + b0.y,
+                      __uint_as_float(a[u * 8 + 2]) + b0.z, __uint_as_float(a[u * 8 + 3]) + b0.w,
+                      __uint_as_float(a[u * 8 + 4]) + b1.x, __uint_as_float(a[u * 8 + 5]) + b1.y,
+                      __uint_as_float(a[u * 8 + 6]) + b1.z, __uint_as_float(a[u * 8 + 7]) + b1.w};
+        if (RELU) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+        }
+        *reinterpret_cast<uint4*>(rowp + ((((uint32_t)(u0 + u)) ^ rsw) << 4)) =
+            make_uint4(pack16x2(v[0], v[1], F16), pack16x2(v[2], v[3], F16), pack16x2(v[4], v[5], F16), pack16x2(v[6], v[7], F16));
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&outready_bar[b]);
+      ++live_tiles;
+      acc ^= 1u;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
 static int encode_act_map(CUtensorMap* m, const void* base, uint64_t C, uint64_t Wd, uint64_t Hd, uint64_t Nd,
@@ -761,6 +984,7 @@ struct ConvTcLaunch {
   int grid;
   int out_bufs;
   int pair;   // 1: conv_tc_pair_kernel (clusters of 2, cta_group::2 MMA)
+  int stem_halo;   // 1: conv_tc_stem_kernel (experimental, NBC_STEM_HALO=1)
 };
 
 // Which launches run on CTA pairs (conv_tc_pair_kernel).  Measured per layer class on B200 (profiles/r01s_*): pairs win
@@ -900,6 +1124,7 @@ static int build_launch(const ConvGeom& g, const void* x, const void* w, const f
     // the prefetch in the kernel touches tmA[0]; make sure it is a valid map
     if (!used[0]) p.tmA[0] = p.tmA[p.tap_map[0]];
   }
+  L->stem_halo = 0;
   L->pair = want_pair(residual != nullptr ? 2 : (p.n_taps > 1 ? 4 : 1), bn, p.n_taps * p.cblocks);
   int rc = encode_weight_map(&p.tmB, w, (uint64_t)p.n_taps * g.Cin, g.Cout, L->pair ? bn / 2 : bn);
   if (rc) return rc;
@@ -982,6 +1207,22 @@ static int launch_pair(const ConvTcLaunch& L, cudaStream_t stream) {
   }
 }
 
+template <bool RELU, bool F16>
+static int launch_stem_one(const ConvTcLaunch& L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    NBC_CUDA(cudaFuncSetAttribute(conv_tc_stem_kernel<RELU, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes));
+    attr_set = true;
+  }
+  NBC_CUDA(launch_tc(conv_tc_stem_kernel<RELU, F16>, L, kStemSmemBytes, stream));
+  count_launch();
+  return 0;
+}
+static int launch_stem(const ConvTcLaunch& L, cudaStream_t stream) {
+  if (L.p.relu) return L.p.f16 ? launch_stem_one<true, true>(L, stream) : launch_stem_one<true, false>(L, stream);
+  return L.p.f16 ? launch_stem_one<false, true>(L, stream) : launch_stem_one<false, false>(L, stream);
+}
+
 template <int BN, int KBLK>
 static int launch_bn(const ConvTcLaunch& L, cudaStream_t stream) {
   const bool res = L.p.residual != nullptr;
@@ -1034,6 +1275,14 @@ int conv_tc_prepare_stem(int N, int Ho, int Wo, int Hp, int Wp, const void* padd
   if (rc) return rc;
   L->out_bufs = 4;
   L->pair = 0;
+  // experimental halo kernel: 128 x 1 tiles only (the production geometry, Wo = 512), opt-in until verified on a GPU
+  static const int halo = [] {
+    const char* e = getenv("NBC_STEM_HALO");
+    return (e && *e) ? atoi(e) : 0;
+  }();
+  p.stem_src = reinterpret_cast<const uint8_t*>(padded);
+  p.stem_hp = Hp, p.stem_wp = Wp;
+  L->stem_halo = (halo == 1 && p.tw == 128 && p.th == 1 && (reinterpret_cast<uintptr_t>(padded) & 15) == 0) ? 1 : 0;
   set_grid(L);
   return 0;
 }
@@ -1096,6 +1345,7 @@ int conv_tc_prepare_dual(const ConvGeom& g, const void* x, const ConvGeom& g2, c
 
 int conv_tc_run(const ConvTcPrepared* prep, cudaStream_t stream) {
   const ConvTcLaunch* L = reinterpret_cast<const ConvTcLaunch*>(prep->storage);
+  if (L->kblk == 32 && L->stem_halo) return launch_stem(*L, stream);
   if (L->kblk == 32) return launch_bn<64, 32>(*L, stream);
   if (L->pair) return L->block_n == 256 ? launch_pair<256>(*L, stream) : launch_pair<128>(*L, stream);
   switch (L->block_n) {

@@ -326,6 +326,30 @@ def test_stem_maxpool_head(cuda_device):
     assert (lg - refl).abs().max() < 1e-4
 
 
+@pytest.mark.skipif(os.environ.get('NBC_TEST_EXPERIMENTAL', '0') != '1' or os.environ.get('NBC_STEM_HALO', '0') != '1',
+                    reason='stem halo kernel: built in round 1, not yet verified on a GPU (NBC_TEST_EXPERIMENTAL=1 NBC_STEM_HALO=1 runs it)')
+def test_stem_halo_kernel(cuda_device):
+    """conv_tc_stem_kernel (overlapping no-swizzle windows out of a 7-row halo) at the production tile geometry (128 x 1
+    output tiles): full-width rows, a width that leaves a partial last tile, a batch, fp16 storage."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(64, 3, 7, 7, generator=g) * 0.1
+    bn = [torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.1, torch.randn(64, generator=g) * 0.1,
+          torch.rand(64, generator=g) + 0.5]
+    scale = bn[0] / torch.sqrt(bn[3] + 1e-5)
+    wf = (w * scale.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).contiguous().to(cuda_device)
+    bf = (bn[1] - bn[2] * scale).to(cuda_device)
+    for (N, H, W, dtype, tol) in [(1, 61, 1024, torch.bfloat16, 0.02), (2, 61, 900, torch.bfloat16, 0.02),
+                                  (3, 333, 1024, torch.bfloat16, 0.02), (1, 61, 1024, torch.float16, 0.003)]:
+        imgs = np.stack([synth.texture_u8(H, W, 10 + i) for i in range(N)])
+        y = ops.stem_tc(torch.from_numpy(imgs).to(cuda_device), omodel.DEFAULT_MEAN, omodel.DEFAULT_STD, wf, bf, dtype=dtype).float().cpu()
+        for i in range(N):
+            r = torch.nn.functional.conv2d(omodel.normalise_u8(imgs[i]), w * scale.view(-1, 1, 1, 1), bn[1] - bn[2] * scale,
+                                           stride=2, padding=3).relu()
+            assert y[i].shape == r[0].permute(1, 2, 0).shape
+            assert (y[i].permute(2, 0, 1) - r[0]).abs().max() < tol * r.abs().max() + 1e-2, (N, H, W, i)
+
+
 # ------------------------------------------------------------------------------------------------- K3 upsample + argmax
 @pytest.mark.parametrize('shape', [(2, 13, 16, 100, 128), (1, 128, 128, 1024, 1024), (1, 77, 128, 611, 1024)])
 def test_upsample_argmax_bit_exact(cuda_device, shape):

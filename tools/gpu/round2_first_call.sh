@@ -25,3 +25,9 @@ ncu -i /tmp/conv_full.ncu-rep --page raw --csv > gpurun_out/conv_full_raw.csv 2>
 python tools/ncu_summarise.py gpurun_out/conv_full_raw.csv gpurun_out/ncu_conv_tc_full.txt gpurun_out/ncu_traffic.json
 # (5) residual 1x1 expansions on 128-column tiles (5 operand stages instead of 3)
 for v in 0 128; do NBC_RES_BN=$v timeout 200 python tools/layer_profile.py 8 624 1024 > gpurun_out/layers_resbn$v.txt 2>&1; echo "NBC_RES_BN=$v"; tail -n 1 gpurun_out/layers_resbn$v.txt; done
+# (6) the stem halo kernel (overlapping no-swizzle windows; never run on a GPU so far): its own test, the model-level tests
+# and the per-layer table with it switched on
+NBC_TEST_EXPERIMENTAL=1 NBC_STEM_HALO=1 timeout 300 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py -q -m gpu --no-header -p no:cacheprovider -x \
+  -k 'stem or ragged or engine or model_parity' > gpurun_out/t_stem_halo.log 2>&1
+echo "stem halo exit $?"; tail -n 5 gpurun_out/t_stem_halo.log
+NBC_STEM_HALO=1 timeout 200 python tools/layer_profile.py 8 624 1024 > gpurun_out/layers_stem_halo.txt 2>&1; head -n 3 gpurun_out/layers_stem_halo.txt; tail -n 1 gpurun_out/layers_stem_halo.txt
