@@ -1,6 +1,7 @@
 """bench.py -- headline benchmark of the B200 segmentation hot path (see the contract in DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload predict64|batch32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload predict64|batch32|train|cli]
+                    [--precision bf16|fp16]
 
 workload predict64 (default, BASELINE.json configs[1]): a "step" is one pass of the predict hot path over a batch
 of 64 synthetic raw 4096x4096x3 scans (BMP pixel arrays: BGR, bottom-up, dark bands) with --exclude_nodes:
