@@ -43,6 +43,20 @@ encode_tiled_fn get_encode_tiled() {
   return fn;
 }
 
+// number of folded weights outside the fp16 range seen by fold_pack_kernel since the last reset (nbc_plan_create refuses
+// an fp16 plan when it is non-zero: a saturated WEIGHT is a wrong network, unlike a saturated activation spike)
+__device__ unsigned int g_fold_overflow = 0;
+
+int fold_overflow_reset() {
+  const unsigned int z = 0;
+  NBC_CUDA(cudaMemcpyToSymbol(g_fold_overflow, &z, sizeof(z)));
+  return 0;
+}
+int fold_overflow_read(unsigned int* n) {
+  NBC_CUDA(cudaMemcpyFromSymbol(n, g_fold_overflow, sizeof(*n)));
+  return 0;
+}
+
 // w f32 OIHW -> bf16 [Cout][kh][kw][cin_pad] scaled by gamma/sqrt(var+eps); bias = beta - mean*scale (+cb*scale)
 __global__ void __launch_bounds__(256) fold_pack_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, const float* __restrict__ mean,
@@ -62,6 +76,7 @@ __global__ void __launch_bounds__(256) fold_pack_kernel(const float* __restrict_
     float v = 0.f;
     if (c < Cin) v = w[(((int64_t)oc * Cin + c) * kh + ky) * kw + kx] * scale;
     if (wp) wp[i] = cvt16(v, f16);
+    if (wp && f16 && !(fabsf(v) <= 65504.f)) atomicAdd(&g_fold_overflow, 1u);
     if (wp_f32) wp_f32[i] = v;
     if (c == 0 && ky == 0 && kx == 0) {
       float b = gamma ? beta[oc] - mean[oc] * scale : 0.f;

@@ -307,13 +307,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
-// 16-bit storage format of activations and weights: f16 == 0 -> bf16 (default), f16 == 1 -> IEEE fp16.  Both feed
-// tcgen05 kind::f16 at the same rate; fp16 keeps 3 more mantissa bits (see DESIGN.md "Numerics").
+// 16-bit storage format of activations and weights: f16 == 1 -> IEEE fp16 (the predict default), f16 == 0 -> bf16
+// (training; opt-in for predict).  Both feed tcgen05 kind::f16 at the same rate; fp16 keeps 3 more mantissa bits (see
+// DESIGN.md "Numerics").  fp16 stores SATURATE: a value beyond +-65504 becomes +-65504, never inf (one F2FP.SATFINITE
+// instruction, same cost as the plain pack), so an activation spike cannot turn the rest of the network into NaNs.
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 __device__ __forceinline__ uint32_t pack16x2(float lo, float hi, int f16) {
-  if (f16) {
-    __half2 h = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&h);
-  }
+  if (f16) return pack_f16x2_sat(lo, hi);
   return pack_bf16x2(lo, hi);
 }
 __device__ __forceinline__ float lo16(uint32_t v, int f16) {
@@ -323,7 +327,12 @@ __device__ __forceinline__ float hi16(uint32_t v, int f16) {
   return f16 ? __half2float(__ushort_as_half((unsigned short)(v >> 16))) : bf16hi(v);
 }
 __device__ __forceinline__ unsigned short cvt16(float x, int f16) {
-  return f16 ? __half_as_ushort(__float2half_rn(x)) : __bfloat16_as_ushort(__float2bfloat16_rn(x));
+  if (f16) {
+    unsigned short h;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+    return h;
+  }
+  return __bfloat16_as_ushort(__float2bfloat16_rn(x));
 }
 
 #endif  // __CUDACC__

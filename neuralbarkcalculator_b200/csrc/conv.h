@@ -54,5 +54,8 @@ int ragged_levels(const int* heights, const int* first_last, int N, int Hc, int*
 int fold_pack(const float* w, const float* gamma, const float* beta, const float* mean, const float* var,
               const float* cb, float eps, int Cout, int Cin, int kh, int kw, int cin_pad, void* wp_bf16, float* wp_f32,
               float* bias, cudaStream_t stream, int f16 = 0);
+// count of folded weights outside the fp16 range since the last reset (fp16 packs saturate; nbc_plan_create checks this)
+int fold_overflow_reset();
+int fold_overflow_read(unsigned int* n);
 
 }  // namespace nbc

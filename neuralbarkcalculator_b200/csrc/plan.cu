@@ -337,8 +337,9 @@ extern "C" nbc_plan* nbc_plan_create(const void* const* t, int n_tensors, const 
   for (int i = 0; i < 3; ++i) p->mean[i] = mean3_host[i], p->std[i] = std3_host[i];
   int rc = 0;
   int idx = 0;
+  if (p->f16) rc = fold_overflow_reset();
   // stem: f32 weights [64][7][7][3]
-  rc = dev_alloc(p, reinterpret_cast<void**>(&p->stem_w), 64 * 147 * 4);
+  if (!rc) rc = dev_alloc(p, reinterpret_cast<void**>(&p->stem_w), 64 * 147 * 4);
   if (!rc) rc = dev_alloc(p, reinterpret_cast<void**>(&p->stem_b), 64 * 4);
   if (!rc)
     rc = fold_pack(reinterpret_cast<const float*>(t[0]), reinterpret_cast<const float*>(t[1]),
@@ -396,6 +397,17 @@ extern "C" nbc_plan* nbc_plan_create(const void* const* t, int n_tensors, const 
     }
   }
   idx += 2;
+  if (!rc && p->f16) {
+    // fp16 storage: a BN-folded weight beyond +-65504 cannot be represented (the pack saturates) -- refuse the plan
+    // instead of running a different network; bf16 storage (f16 = 0) has the f32 exponent range
+    unsigned int over = 0;
+    rc = fold_overflow_read(&over);
+    if (!rc && over) {
+      set_error("nbc_plan_create: %u BN-folded weights exceed the fp16 range (|w| > 65504); build the plan with bf16 "
+                "storage (f16 = 0, precision='bf16')", over);
+      rc = NBC_ERR_INVALID;
+    }
+  }
   if (rc || idx != 326) {
     if (!rc) set_error("nbc_plan_create: internal tensor walk ended at %d", idx);
     nbc_plan_destroy(p);

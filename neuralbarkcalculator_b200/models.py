@@ -22,6 +22,13 @@ from . import ops
 from .dataset import RegressionDatasetFolder, make_dataset, pil_loader, read_bmp_pixels
 
 
+# 16-bit storage format of activations / packed weights of the predict path.  fp16: same tcgen05 rate as bf16, 3 more
+# mantissa bits -- the format that meets the parity bar against the reference's f32 forward (argmax agreement >= 99.9 %,
+# percentages within 0.1 pp; profiles/r02_parity.md); stores saturate at +-65504 and a plan whose BN-folded weights do not
+# fit the fp16 range is refused (use 'bf16', which has the f32 exponent range and 8x the rounding error).
+DEFAULT_PRECISION = 'fp16'
+
+
 class FCNHead(nn.Sequential):
     """Parameter container with the layout of models.py:113-124 (conv3x3, BN, ReLU, Dropout, conv1x1+bias)."""
 
@@ -43,7 +50,7 @@ class SimpleSegmentationModel(nn.Module):
         self._plan_key = None
         self._mean = list(mean) if mean is not None else [0.0, 0.0, 0.0]
         self._std = list(std) if std is not None else [1.0, 1.0, 1.0]
-        self._precision = 'bf16'
+        self._precision = DEFAULT_PRECISION
 
     # -- native plan management ------------------------------------------------------------------------------
     def _state_key(self):
@@ -71,8 +78,8 @@ class SimpleSegmentationModel(nn.Module):
         self._plan = None
 
     def set_precision(self, precision):
-        """16-bit storage format of activations / packed weights on the tensor cores: 'bf16' (default) or 'fp16'
-        (same speed, 8x smaller rounding error; range is ample for BN-folded ResNet activations)."""
+        """16-bit storage format of activations / packed weights on the tensor cores: 'fp16' (default, see
+        DEFAULT_PRECISION) or 'bf16' (same speed, 8x the rounding error, f32 exponent range)."""
         if precision not in ('bf16', 'fp16'):
             raise ValueError("precision must be 'bf16' or 'fp16'")
         if precision != self._precision:
@@ -144,17 +151,12 @@ class Preprocessor():
         raw = t.pin_memory().to(self.device, non_blocking=True) if t.numel() > (1 << 20) else t.to(self.device)
         if max(H, W) > self.target_size:
             if H != 4 * self.target_size or W != 4 * self.target_size:
-                if os.environ.get('NBC_GENERAL_RESIZE', '0') == '1':
-                    # general-ratio kernel (f64 restatement of skimage's order-3 resize): built in round 1 but not yet
-                    # verified on a GPU, hence opt-in
-                    out, fl = ops.preprocess_general(raw, H, W, self.target_size, pitch, bgr=bgr, bottom_up=bottom_up)
-                    first, last = fl.tolist()
-                    T = self.target_size
-                    return out[:(last - first) * T * 3].view(last - first, T, 3)
-                raise NotImplementedError(
-                    'only the 4x reduction %dx%d -> %dx%d is enabled (got %dx%d); no fallback resize '
-                    '(NBC_GENERAL_RESIZE=1 opts into the experimental general-ratio kernel)'
-                    % (4 * self.target_size, 4 * self.target_size, self.target_size, self.target_size, H, W))
+                # any other size: the general-ratio kernel (f64 restatement of skimage's order-3 resize, models.py:194-198);
+                # the result is target x target, i.e. square, so trim_black applies (models.py:200)
+                out, fl = ops.preprocess_general(raw, H, W, self.target_size, pitch, bgr=bgr, bottom_up=bottom_up)
+                first, last = fl.tolist()
+                T = self.target_size
+                return out[:(last - first) * T * 3].view(last - first, T, 3)
             out, fl = ops.preprocess_4x(raw, H, W, pitch, bgr=bgr, bottom_up=bottom_up)
             first, last = fl.tolist()
             Wo = W // 4
@@ -201,7 +203,7 @@ class NeuralBarkCalculator():
     DEFAULT_MM_PER_PIXEL = 3.6 * 3.6
 
     def __init__(self, model_path, device, mean=DEFAULT_MEAN, std=DEFAULT_STD, target_size=1024,
-                 mm_per_pix=DEFAULT_MM_PER_PIXEL, state_dict=None, precision='bf16', load_weights=True):
+                 mm_per_pix=DEFAULT_MM_PER_PIXEL, state_dict=None, precision=DEFAULT_PRECISION, load_weights=True):
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise RuntimeError("device '%s': this build runs on CUDA (B200) only -- no CPU path" % device)

@@ -422,7 +422,7 @@ def confusion_matrix(pred_u8, target):
 class Plan:
     """Owns an nbc_plan (BN-folded bf16 weights on the device) built from the 326 state_dict tensors."""
 
-    def __init__(self, tensors, mean, std, device, precision='bf16'):
+    def __init__(self, tensors, mean, std, device, precision='fp16'):
         lib = _lib.load()
         if precision not in HALF_DTYPES:
             raise ValueError("precision must be 'bf16' or 'fp16'")

@@ -44,3 +44,14 @@ def synthetic_sd():
     from oracle import model as omodel
     g = np.load(os.path.join(GOLDEN, 'model_small.npz'))
     return omodel.synthetic_state_dict(seed=int(g['state_dict_seed']), head=(g['head_w'], g['head_b']))
+
+
+@pytest.fixture(scope='session')
+def trained_like_sd():
+    """Synthetic state_dict conditioned like a TRAINED ResNet (the last BatchNorm of every bottleneck has gain 0.1, cf.
+    torchvision's zero_init_residual; the classifier is three random directions on the standardised head features, the
+    noise gain of an ordinary linear layer) with unit-scale logits (overall std ~1).  The network the north_star
+    floating-point bar is gated on (tests/test_gpu_model.py)."""
+    from oracle import model as omodel
+    return omodel.synthetic_state_dict(seed=3, branch_gain=0.1, calibration='features', logit_std=0.6,
+                                       class_bias=(0.8, 0.1, -1.1))

@@ -82,8 +82,6 @@ def test_preprocess_full_size_and_edges(cuda_device):
     assert (first, last) == (0, 16) and np.array_equal(out, expect)
 
 
-@pytest.mark.skipif(os.environ.get('NBC_TEST_EXPERIMENTAL', '0') != '1',
-                    reason='general-ratio resize kernel: built in round 1, not yet verified on a GPU (NBC_TEST_EXPERIMENTAL=1 runs it)')
 def test_preprocess_general_ratio(cuda_device):
     """Any size -> target x target (models.py:194-198) against the f64 restatement, byte for byte: non-integer ratios both
     ways, upscaling of one axis, BGR / bottom-up sources, dark bands that trigger the trim, an input range that clips."""

@@ -14,22 +14,27 @@ from oracle import synth
 pytestmark = pytest.mark.gpu
 IMPLS = [int(v) for v in os.environ.get('NBC_TEST_IMPLS', '2,1').split(',')]   # 1 = tcgen05, 2 = mma.sync
 
-# Tolerances for bf16 activations through 53 convolutions against the f32 oracle, on logits calibrated to
-# std ~1.2 per class (oracle/model.py synthetic_state_dict).  north_star quotes max-abs <= 2e-2 and argmax agreement
-# >= 99.9 %; see DESIGN.md "Numerics" for what is measured and why near-ties decide the agreement.
-# bf16 operands inject ~0.16 % rms relative error per layer; over 53 layers that is ~1 % of the logit scale.
-# Measured on B200 (profiles/r01_parity.md): bf16 mean 0.7-2.1 %, max 4.6-12 % of the logit std.
+# ---- floating-point parity bar ------------------------------------------------------------------------------------
+# north_star (BASELINE.json): logits max-abs <= 2e-2 vs the f32 forward of the reference, argmax agreement >= 99.9 % of
+# pixels, bark / node percentages within 0.1 pp.  The DEFAULT storage precision of the predict path (fp16) is gated on
+# exactly those numbers on (1) the reference-pinned golden fixture, (2) a network conditioned like a trained ResNet at
+# 1024x1024 and (3) the same network on a trimmed 611-row image (`trained_like_sd`, overall logit std ~1 -- the absolute
+# 2e-2 is a statement about unit-scale logits; the error is proportional to the logit scale, 1.5-2 % of it).
+NORTH_STAR = {'max_abs': 2e-2, 'agree': 0.999, 'pp': 0.1}
+DEFAULT_PRECISION = 'fp16'
+# The seed-0 "harsh" network of the other tests (whitened head: cov^(-1/2) blows up the noisy low-variance directions;
+# every block re-mixes 50 % of the stream) is a STRESS case: reported, and bounded only as a regression guard.
 # precision -> (max-abs / std, mean-abs / std, argmax agreement, percentage points after region removal)
-TOL = {'bf16': (0.20, 0.03, 0.98, 0.75),
-       'fp16': (0.02, 0.004, 0.997, 0.1)}      # north_star: max-abs <= 2e-2 (std ~1.5), 0.1 pp; agreement see DESIGN.md
-# (max-abs, argmax agreement, percentage points) on the trained-like network; north_star: 2e-2, 0.999, 0.1
-# measured on B200 (profiles/r01_parity.md): fp16 storage meets the agreement and percentage targets at gain 0.1
-NORTH_STAR_TRAINED_LIKE = {('bf16', 0.1): (0.5, 0.992, 0.45), ('bf16', 0.5): (0.4, 0.98, 0.35),
-                           ('fp16', 0.1): (0.05, 0.999, 0.1), ('fp16', 0.5): (0.05, 0.997, 0.15)}
-PRECISIONS = os.environ.get('NBC_TEST_PRECISIONS', 'bf16,fp16').split(',')
+# measured on B200: fp16 1.2 % / 0.22 % / 99.80 % / 0.088 pp; bf16 12 % / 2.1 % / 98.5 % / 0.47 pp (profiles/r02_parity.md)
+TOL = {'fp16': (0.02, 0.004, 0.997, 0.1),
+       'bf16': (0.20, 0.03, 0.98, 0.75)}
+# trained-like conditioning at logit std ~2 (report + regression guard): (max-abs, argmax agreement, percentage points)
+TRAINED_LIKE_STD2 = {('bf16', 0.1): (0.5, 0.992, 0.45), ('bf16', 0.5): (0.4, 0.98, 0.35),
+                     ('fp16', 0.1): (0.05, 0.999, 0.1), ('fp16', 0.5): (0.05, 0.997, 0.15)}
+PRECISIONS = os.environ.get('NBC_TEST_PRECISIONS', 'fp16,bf16').split(',')
 
 
-def _model(sd, dev, precision='bf16'):
+def _model(sd, dev, precision=DEFAULT_PRECISION):
     import neuralbarkcalculator_b200 as nbc
     m = nbc.fcn_resnet50(pretrained=False)
     m.load_state_dict(sd, strict=True)
@@ -39,7 +44,7 @@ def _model(sd, dev, precision='bf16'):
     return m
 
 
-def _report(name, got, ref, precision='bf16'):
+def _report(name, got, ref, precision=DEFAULT_PRECISION):
     err = np.abs(got - ref)
     print('\n[%s %s] logits: max-abs %.4g mean-abs %.4g (ref std %.3g) -> relative max %.4f mean %.5f'
           % (name, precision, err.max(), err.mean(), ref.std(), err.max() / ref.std(), err.mean() / ref.std()))
@@ -58,6 +63,8 @@ def test_model_golden_small(cuda_device, golden_dir, synthetic_sd, impl, precisi
     img = torch.from_numpy(g['image']).unsqueeze(0).to(cuda_device)
     low = m.lowres_logits_u8(img).cpu().numpy()
     err = _report('golden small impl=%d' % impl, low, g['lowres_logits'], precision)
+    if precision == DEFAULT_PRECISION:      # reference-pinned fixture: the north_star numbers themselves
+        assert err.max() <= NORTH_STAR['max_abs']
     # drop-in forward: normalised f32 NCHW in, full-resolution f32 logits out (models.py:33-43)
     x = omodel.normalise_u8(g['image']).to(cuda_device)
     full = m(x).cpu().numpy()
@@ -66,7 +73,7 @@ def test_model_golden_small(cuda_device, golden_dir, synthetic_sd, impl, precisi
     mask = m.predict_mask_u8(img).cpu().numpy()[0]
     agree = (mask == g['mask'][0]).mean()
     print('[golden small impl=%d %s] argmax agreement %.5f' % (impl, precision, agree))
-    assert agree >= TOL[precision][2] - (0.002 if precision == 'fp16' else 0)   # 15k pixels: 0.1 % is 15 pixels
+    assert agree >= (NORTH_STAR['agree'] if precision == DEFAULT_PRECISION else TOL[precision][2])
 
 
 @pytest.mark.parametrize('precision', PRECISIONS)
@@ -104,6 +111,60 @@ def test_model_full_size_vs_oracle(cuda_device, synthetic_sd, precision):
             pp = 100.0 * abs(int(counts[0, c]) - int((ref_clean == c).sum())) / mask.size
             print('[%dx%d %s] class %d percentage diff %.4f pp' % (H, W, precision, c, pp))
             assert pp < TOL[precision][3]
+
+
+def test_model_north_star_default_precision(cuda_device, trained_like_sd):
+    """THE floating-point gate (north_star): default storage precision, tcgen05 path, trained-like network, one 1024x1024
+    image and one trimmed 611-row image against the reference's f32 forward (CPU oracle): logits max-abs <= 2e-2, argmax
+    agreement >= 99.9 % of pixels, bark / node percentages after region removal within 0.1 pp."""
+    from neuralbarkcalculator_b200 import ops
+    m = _model(trained_like_sd, cuda_device)
+    assert m._precision == DEFAULT_PRECISION
+    net = omodel.load_model(trained_like_sd)
+    for seed, (H, W) in ((31, (1024, 1024)), (32, (611, 1024))):
+        img = synth.texture_u8(H, W, seed)
+        with torch.no_grad():
+            ref_low = omodel.lowres_logits(net, omodel.normalise_u8(img))
+        ref_up, ref_mask = omodel.upsample_argmax(ref_low, (H, W))
+        ref_mask = ref_mask[0].numpy()
+        t = torch.from_numpy(img).unsqueeze(0).to(cuda_device)
+        low = m.lowres_logits_u8(t)
+        err = np.abs(low.cpu().numpy() - ref_low.numpy())
+        full_err = (ops.upsample_bicubic(low, (H, W)).cpu() - ref_up).abs().max().item()
+        mask = m.predict_mask_u8(t)
+        agree = (mask.cpu().numpy()[0] == ref_mask).mean()
+        _, counts = ops.remove_small_zones_u8(mask.clone())
+        ref_clean = opost.remove_small_zones_2d(ref_mask)
+        pps = [100.0 * abs(int(counts[0, c]) - int((ref_clean == c).sum())) / ref_mask.size for c in (1, 2)]
+        print('\n[north star %dx%d %s] logit std %.3f: max-abs %.4g (full-res %.4g) mean-abs %.4g; argmax agreement %.5f; '
+              'bark / node off by %.4f / %.4f pp' % (H, W, DEFAULT_PRECISION, ref_low.numpy().std(), err.max(), full_err, err.mean(),
+                                                     agree, pps[0], pps[1]))
+        assert err.max() <= NORTH_STAR['max_abs'] and full_err <= NORTH_STAR['max_abs']
+        assert agree >= NORTH_STAR['agree']
+        assert max(pps) <= NORTH_STAR['pp']
+
+
+def test_fp16_saturates_instead_of_overflowing(cuda_device, synthetic_sd):
+    """fp16 storage has a 65 504 ceiling.  (1) A BatchNorm gain that drives activations far beyond it: every 16-bit store
+    saturates (F2FP.SATFINITE), so the logits stay finite -- no inf, no NaN -- where a plain fp16 pack would give inf and
+    then NaN (inf - inf in the next layer).  (2) BN-folded WEIGHTS beyond the range would be a different network: the plan
+    is refused with a pointer to precision='bf16', and the bf16 plan of that network runs."""
+    sd = {k: v.clone() for k, v in synthetic_sd.items()}
+    sd['backbone.layer1.0.bn2.weight'].mul_(3.0e4)       # activations ~1e5 >> 65504, folded weights still < 65504
+    img = torch.from_numpy(synth.texture_u8(128, 256, 5)).unsqueeze(0).to(cuda_device)
+    net = omodel.load_model(sd)
+    with torch.no_grad():
+        peak = net.backbone.layer1[0].relu(net.backbone.layer1[0].bn2(net.backbone.layer1[0].conv2(net.backbone.layer1[0].relu(
+            net.backbone.layer1[0].bn1(net.backbone.layer1[0].conv1(net.backbone.maxpool(net.backbone.relu(net.backbone.bn1(
+                net.backbone.conv1(omodel.normalise_u8(img[0].cpu().numpy()))))))))))).max().item()
+    assert peak > 65504.0, 'the test network must overflow fp16 (peak %g)' % peak
+    low = _model(sd, cuda_device, 'fp16').lowres_logits_u8(img)
+    assert torch.isfinite(low).all(), 'fp16 stores must saturate, not overflow'
+    sd2 = {k: v.clone() for k, v in synthetic_sd.items()}
+    sd2['backbone.layer2.1.bn1.weight'].mul_(1.0e7)      # folded weights ~1e6: not representable in fp16
+    with pytest.raises(RuntimeError, match='fp16 range'):
+        _model(sd2, cuda_device, 'fp16').lowres_logits_u8(img)
+    assert torch.isfinite(_model(sd2, cuda_device, 'bf16').lowres_logits_u8(img)).all()
 
 
 def test_batch_equals_single(cuda_device, synthetic_sd):
@@ -176,8 +237,10 @@ def test_engine_matches_per_image_path(cuda_device, synthetic_sd):
         assert counts_h[i].tolist() == cnt.cpu().tolist()
 
 
-def test_predict_pipeline_matches_oracle(cuda_device, synthetic_sd, tmp_path):
-    """predict.py end to end on a tiny synthetic folder: processed PNGs, dual PNGs and CSV against the CPU oracle."""
+def test_predict_pipeline_matches_oracle(cuda_device, trained_like_sd, tmp_path):
+    """predict.py end to end on a tiny synthetic folder: processed PNGs (bit-exact), dual PNGs (>= 99.9 % of pixels) and
+    CSV percentages (within 0.1 pp) against the CPU oracle -- north_star's bar, default precision."""
+    synthetic_sd = trained_like_sd
     import neuralbarkcalculator_b200 as nbc
     from neuralbarkcalculator_b200 import predict as npredict
     from PIL import Image
@@ -200,9 +263,11 @@ def test_predict_pipeline_matches_oracle(cuda_device, synthetic_sd, tmp_path):
             da = np.asarray(Image.open(os.path.join(root, 'results', 'outputs', wood, fn)))
             db = np.asarray(Image.open(os.path.join(root_ref, 'results', 'outputs', wood, fn)))
             assert set(np.unique(da)) <= {0, 127, 255} and da.shape == db.shape
-            assert (da == db).mean() >= TOL['bf16'][2]
+            agree = (da == db).mean()
+            print('[pipeline %s] dual image agreement %.5f' % (fn, agree))
+            assert agree >= NORTH_STAR['agree']
     for a, b in zip(rows[1:], rows_ref[1:]):
-        assert abs(float(a[2]) - float(b[2])) < 0.5 and float(a[4]) == 0.0 and float(b[4]) == 0.0
+        assert abs(float(a[2]) - float(b[2])) <= NORTH_STAR['pp'] and float(a[4]) == 0.0 and float(b[4]) == 0.0
     with open(os.path.join(root, 'results', 'final_stats.csv')) as f:
         got = list(csv.reader(f, delimiter='\t'))
     assert got[0] == opost.CSV_HEADER and len(got) == 4 and all(len(r) == 6 for r in got[1:])
@@ -282,5 +347,5 @@ def test_model_parity_trained_like_conditioning(cuda_device, precision, branch_g
     pps = [100.0 * abs(int(counts[0, c]) - int((ref_clean == c).sum())) / mask.size for c in (1, 2)]
     print('\n[trained-like %s gain %.1f] logits std %.3f: max-abs %.4g mean-abs %.4g; argmax agreement %.5f; class percentages off by %.4f / %.4f pp'
           % (precision, branch_gain, ref_low.numpy().std(), err.max(), err.mean(), agree, pps[0], pps[1]))
-    lim = NORTH_STAR_TRAINED_LIKE[(precision, branch_gain)]
+    lim = TRAINED_LIKE_STD2[(precision, branch_gain)]
     assert err.max() <= lim[0] and agree >= lim[1] and max(pps) <= lim[2]
