@@ -444,10 +444,15 @@ def main():
             def drain_host():
                 while pending:
                     res['rows'], res['counts'], _ = eng.collect(pending.pop(0))
+            h0 = eng.h2d_bytes
             ms_h, _ = timed(step_host, args.steps, max(1, args.warmup), drain_host)
             d2h = int(B * 1024 * 1024 + B * 12 + B * 8)     # mask canvases + counts + {first,last}
+            # bytes the engine really copied per step (counted from the tensors it copies): the scans' all-zero dark bands
+            # stay on the host (engine.py; NBC_ZERO_SPAN=0 copies everything)
+            h2d = int((eng.h2d_bytes - h0) // (args.steps + max(1, args.warmup)))
             e2e = {'value': world * B * args.steps / (ms_h / 1000.0), 'unit': 'images/s',
-                   'h2d_bytes_per_step': B * RAW * RAW * 3, 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_h / args.steps}
+                   'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_h / args.steps,
+                   'raw_bytes_per_step': B * RAW * RAW * 3, 'zero_band_rows_skipped': bool(eng.zero_span)}
 
     value = world * n_img * args.steps / (ms / 1000.0)
 

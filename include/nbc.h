@@ -53,12 +53,20 @@ int64_t nbc_launch_count(void);
 size_t nbc_preprocess_workspace_bytes(int H, int W);
 int nbc_preprocess_4x_u8(const uint8_t* raw, int H, int W, int64_t pitch, int flags, uint8_t* out,
                          int32_t* first_last, void* workspace, size_t workspace_bytes, void* stream);
+/* Same, for a scan whose dark bands never left the host: raw_span points at memory row span_row0 and holds span_rows
+ * rows (both multiples of 4); every other row of the H x W image is all zero by definition and is never read.  The
+ * result is bit-identical to nbc_preprocess_4x_u8 on the full image (global min / max clip included).
+ * nbc_host_zero_row_span (HOST memory, plain C++, no GPU) finds that span: the rows before the first and after the
+ * last row with a non-zero byte, widened outwards to whole groups of `group` rows; rows = 0 for an all-zero image. */
+int nbc_preprocess_4x_span_u8(const uint8_t* raw_span, int H, int W, int64_t pitch, int flags, int span_row0, int span_rows,
+                              uint8_t* out, int32_t* first_last, void* workspace, size_t workspace_bytes, void* stream);
+int nbc_host_zero_row_span(const uint8_t* raw, int H, int64_t pitch, int64_t row_bytes, int group, int32_t* row0,
+                           int32_t* rows);
 /* General ratio: any H x W image whose larger side exceeds `target` becomes target x target (models.py:194-198,
  * skimage resize order 3, mode 'reflect', no anti-aliasing, clipped to the input range), then trim_black and the
  * float -> u8 rounding -- float64 arithmetic in the order of oracle/preprocess.py::resize_general_f64.  Same flags,
  * outputs and conventions as nbc_preprocess_4x_u8; out capacity target*target*3.
- * EXPERIMENTAL in round 1: built and compiled, not yet run on a GPU (the Python mirror only routes to it when
- * NBC_GENERAL_RESIZE=1; otherwise non-4x sizes are rejected loudly). */
+ * The Python mirror (Preprocessor) routes every size other than exactly 4 * target squared to it. */
 size_t nbc_preprocess_general_workspace_bytes(int H, int W, int target);
 int nbc_preprocess_general_u8(const uint8_t* raw, int H, int W, int64_t pitch, int flags, int target, uint8_t* out,
                               int32_t* first_last, void* workspace, size_t workspace_bytes, void* stream);

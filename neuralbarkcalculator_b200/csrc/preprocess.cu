@@ -63,10 +63,13 @@ __device__ __forceinline__ void pass1_load(const uint8_t* __restrict__ raw, int 
 // clamps to the input range [lo, hi], a sub-interval, so clamp(clamp(v, 0, 255), lo, hi) == clamp(v, lo, hi) -- staged
 // through shared memory so that a warp's 384 output bytes go out as 24 coalesced 16-byte stores instead of 384 two-byte
 // ones (the partial-sector writes of the first version cost more than the 50 MB of reads).
+// span_lo / span_hi: the memory rows [span_lo, span_hi) are the ones `raw` really holds (multiples of 4); every other row
+// is all zero BY DEFINITION (the host found the scan's dark bands, nbc_host_zero_row_span, and copied only the rows in
+// between) -- such a group of four rows is never dereferenced and contributes min = max = 0, S = 0.
 template <bool kAligned>
 __global__ void __launch_bounds__(256) resize4x_pass1(const uint8_t* __restrict__ raw, int H, int W, int64_t pitch,
                                                       int flags, uint8_t* __restrict__ r8, PreHeader* hdr,
-                                                      int* __restrict__ rowcount) {
+                                                      int* __restrict__ rowcount, int span_lo, int span_hi) {
   __shared__ __align__(16) uint32_t s_out[8][96];   // per warp: 32 threads x 12 bytes
   const int Wo = W >> 2;
   const int groups = (Wo + 3) >> 2;  // 4 output pixels per thread
@@ -76,10 +79,13 @@ __global__ void __launch_bounds__(256) resize4x_pass1(const uint8_t* __restrict_
   const int wo0 = g << 2;
   const int npx = active ? min(4, Wo - wo0) : 0;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int mem_row = 4 * ((flags & 2) ? (H >> 2) - 1 - ho : ho);     // first memory row of this output row's group
+  const bool zero_rows = mem_row < span_lo || mem_row >= span_hi;
   uint32_t mn2 = 0xFFFFFFFFu, mx2 = 0u;   // min / max as two 16-bit fields
   int nondark = 0;
   uint32_t packed[3] = {0u, 0u, 0u};      // the thread's 12 output bytes (4 pixels x RGB)
-  if (active) {
+  if (active && zero_rows) mn2 = 0u;
+  if (active && !zero_rows) {
     uint32_t cur[4][12];
     pass1_load<kAligned>(raw, H, pitch, flags, ho, wo0, npx, cur);
     // Vertical pass on PACKED 16-bit fields: each word (4 bytes of one row) is widened to two words of two 16-bit
@@ -343,8 +349,19 @@ extern "C" size_t nbc_preprocess_workspace_bytes(int H, int W) {
 
 extern "C" int nbc_preprocess_4x_u8(const uint8_t* raw, int H, int W, int64_t pitch, int flags, uint8_t* out,
                                     int32_t* first_last, void* workspace, size_t workspace_bytes, void* stream_) {
+  return nbc_preprocess_4x_span_u8(raw, H, W, pitch, flags, 0, H, out, first_last, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int nbc_preprocess_4x_span_u8(const uint8_t* raw_span, int H, int W, int64_t pitch, int flags, int span_row0,
+                                         int span_rows, uint8_t* out, int32_t* first_last, void* workspace,
+                                         size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  NBC_REQUIRE(raw && out && first_last && workspace, "nbc_preprocess_4x_u8: null pointer");
+  NBC_REQUIRE((raw_span || span_rows == 0) && out && first_last && workspace, "nbc_preprocess_4x_u8: null pointer");
+  NBC_REQUIRE(span_row0 >= 0 && span_rows >= 0 && span_row0 % 4 == 0 && span_rows % 4 == 0 && span_row0 + span_rows <= H,
+              "nbc_preprocess_4x_span_u8: the span [%d, +%d) must be made of whole groups of 4 rows inside the image", span_row0,
+              span_rows);
+  // the kernel addresses memory row r at raw + r * pitch and never touches a row outside the span
+  const uint8_t* raw = raw_span ? raw_span - (int64_t)span_row0 * pitch : reinterpret_cast<const uint8_t*>(workspace);
   NBC_REQUIRE(H > 0 && W > 0 && H % 4 == 0 && W % 4 == 0, "nbc_preprocess_4x_u8: H and W must be multiples of 4 (got %dx%d)", H, W);
   NBC_REQUIRE(pitch >= (int64_t)W * 3, "nbc_preprocess_4x_u8: pitch %lld < 3*W", (long long)pitch);
   if (workspace_bytes < nbc_preprocess_workspace_bytes(H, W)) {
@@ -361,9 +378,9 @@ extern "C" int nbc_preprocess_4x_u8(const uint8_t* raw, int H, int W, int64_t pi
   dim3 grid(ceil_div(groups, 256), Ho);
   const bool aligned = (reinterpret_cast<uintptr_t>(raw) % 16 == 0) && (pitch % 16 == 0);
   if (aligned)
-    resize4x_pass1<true><<<grid, 256, 0, stream>>>(raw, H, W, pitch, flags, r8, hdr, rowcount);
+    resize4x_pass1<true><<<grid, 256, 0, stream>>>(raw, H, W, pitch, flags, r8, hdr, rowcount, span_row0, span_row0 + span_rows);
   else
-    resize4x_pass1<false><<<grid, 256, 0, stream>>>(raw, H, W, pitch, flags, r8, hdr, rowcount);
+    resize4x_pass1<false><<<grid, 256, 0, stream>>>(raw, H, W, pitch, flags, r8, hdr, rowcount, span_row0, span_row0 + span_rows);
   NBC_CHECK_LAUNCH();
   trim_rows_kernel<<<1, 1024, 0, stream>>>(rowcount, hdr, Ho, Wo, Ho == Wo ? 1 : 0, first_last);
   NBC_CHECK_LAUNCH();

@@ -8,9 +8,16 @@ kernel reads the per-image heights K1 produced on the device), so nothing is rea
 ``run_host`` is the public end-to-end entry (pinned host buffers in, host masks out).  ``submit_host`` / ``collect``
 are its asynchronous halves: a submitted batch only enqueues work, so the host->device copies of the NEXT batch run
 under the network passes of the current one (two buffer slots) and the PCIe link -- the end-to-end bound, 50 MB per
-scan -- never idles between batches."""
+scan -- never idles between batches.
+
+Dark bands stay on the host: the rows of a scan above and below the bark that are EXACTLY zero (what trim_black removes)
+resize to exact zeros, so ``submit_host`` finds them with a host scan (``nbc_host_zero_row_span``, a few worker threads,
+GIL released), copies only the rows in between -- still one ``cudaMemcpyAsync`` per scan -- and K1 treats the rest as
+zeros (``nbc_preprocess_4x_span_u8``).  Bit-identical to copying the whole scan (global min / max clip included);
+``NBC_ZERO_SPAN=0`` switches it off."""
 import ctypes as C
 import os
+from concurrent.futures import ThreadPoolExecutor
 
 import torch
 
@@ -18,7 +25,7 @@ from . import ops
 
 
 # images per ragged batch: the per-launch cost of the 53 network kernels (launch gap, pipeline fill and drain, the last
-# partial wave) is amortised over the chunk -- 0.631 ms per image at 8, 0.608 at 12 (profiles/r01s_chunk_sweep.txt)
+# partial wave) is amortised over the chunk -- 0.631 ms per image at 8, 0.608 at 12 (profiles/r01t_pdl_chunk_depth_sweep.txt)
 DEFAULT_CHUNK = 8
 # raw-scan staging buffers of the host path (50 MB each): the H2D stream runs this many scans ahead of K1
 DEFAULT_STAGE_DEPTH = 4
@@ -62,6 +69,9 @@ class PredictEngine:
         self.out_w = raw_size // 4
         self.chunk = chunk
         self.depth = depth
+        self.zero_span = os.environ.get('NBC_ZERO_SPAN', '1') != '0'
+        self._scan_pool = None
+        self.h2d_bytes = 0        # raw-scan bytes really copied host -> device so far
         self._slots = [None, None]
         self._calls = 0
         self._chunks = 0          # chunks issued so far (logits double buffer)
@@ -105,14 +115,37 @@ class PredictEngine:
         self._logits_free = [None, None]
         return True
 
-    def _preprocess_into(self, slot, i, raw, bgr, bottom_up):
+    def _preprocess_into(self, slot, i, raw, bgr, bottom_up, span=None):
+        """K1 on the current stream.  span = (row0, rows): ``raw`` holds only those memory rows of the scan, the others are
+        all zero (see the module docstring)."""
         lib = ops._lib.load()
         S = self.raw_size
-        ops._lib.check(lib.nbc_preprocess_4x_u8(C.c_void_p(raw.data_ptr()), S, S, S * 3, (1 if bgr else 0) | (2 if bottom_up else 0),
-                                                C.c_void_p(slot.proc[i].data_ptr()), C.c_void_p(slot.fl[i].data_ptr()),
-                                                C.c_void_p(self._pre_ws.data_ptr()), self._pre_ws.numel(),
-                                                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
-                       'nbc_preprocess_4x_u8')
+        row0, rows = span if span is not None else (0, S)
+        ops._lib.check(lib.nbc_preprocess_4x_span_u8(C.c_void_p(raw.data_ptr()), S, S, S * 3, (1 if bgr else 0) | (2 if bottom_up else 0),
+                                                     row0, rows, C.c_void_p(slot.proc[i].data_ptr()), C.c_void_p(slot.fl[i].data_ptr()),
+                                                     C.c_void_p(self._pre_ws.data_ptr()), self._pre_ws.numel(),
+                                                     C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
+                       'nbc_preprocess_4x_span_u8')
+
+    def _scan(self, raw):
+        """(row0, rows) of a host scan: the memory rows between its all-zero bands, in whole groups of 4."""
+        S = self.raw_size
+        r0, rows = C.c_int32(0), C.c_int32(0)
+        ops._lib.check(ops._lib.load().nbc_host_zero_row_span(C.c_void_p(raw.data_ptr()), S, S * 3, S * 3, 4, C.byref(r0), C.byref(rows)),
+                       'nbc_host_zero_row_span')
+        return r0.value, rows.value
+
+    def _spans(self, n, get_raw, spans):
+        """Per-scan (row0, rows) futures for a host batch: given by the caller, scanned by the worker threads, or the whole
+        scan when the zero-band path is off."""
+        S = self.raw_size
+        if spans is not None:
+            return [(lambda v=v: v) for v in spans]
+        if not self.zero_span:
+            return [(lambda: (0, S))] * n
+        if self._scan_pool is None:
+            self._scan_pool = ThreadPoolExecutor(int(os.environ.get('NBC_SCAN_THREADS', 4)), thread_name_prefix='nbc-scan')
+        return [self._scan_pool.submit(self._scan, get_raw(i)).result for i in range(n)]
 
     def _segment_chunk(self, slot, a, b, exclude_nodes):
         """Images a..b-1 as ONE ragged batch: network, K3 and K5 read the per-image heights on the device.  The network
@@ -139,7 +172,8 @@ class PredictEngine:
             done.record(self._post_stream)
         return done
 
-    def _run(self, n, get_raw, masks_host, bgr, bottom_up, exclude_nodes, on_device, want_processed=False, only_preprocess=False):
+    def _run(self, n, get_raw, masks_host, bgr, bottom_up, exclude_nodes, on_device, want_processed=False, only_preprocess=False,
+             spans=None):
         """Software pipeline over chunks of images, with NO host synchronisation inside:
              copy stream : H2D of the raw scans (host path only), ``depth`` staging buffers
              pre stream  : K1 + heights for chunk c+1
@@ -162,19 +196,24 @@ class PredictEngine:
             if slot.done is not None:
                 self._pre_stream.wait_event(slot.done)   # the batch that used this slot two calls ago is fully drained
             chunks = [(a, min(a + chunk, n)) for a in range(0, n, chunk)]
+            span_of = None if on_device else self._spans(n, get_raw, spans)
+            pitch = self.raw_size * 3
             for (a, b) in chunks:
                 for i in range(a, b):
                     raw = get_raw(i)
                     if not raw.is_cuda:
                         k = self._issued % depth
+                        row0, rows = span_of[i]()
                         with torch.cuda.stream(self._copy_stream):
                             if self._issued >= depth:
                                 self._copy_stream.wait_event(self._freed[k])
-                            self._stage[k].copy_(raw, non_blocking=True)
+                            if rows:      # one cudaMemcpyAsync per scan: the rows between the dark bands
+                                self._stage[k][:rows * pitch].copy_(raw[row0 * pitch:(row0 + rows) * pitch], non_blocking=True)
                             self._staged[k].record(self._copy_stream)
+                        self.h2d_bytes += rows * pitch
                         self._pre_stream.wait_event(self._staged[k])
                         with torch.cuda.stream(self._pre_stream):
-                            self._preprocess_into(slot, i, self._stage[k], bgr, bottom_up)
+                            self._preprocess_into(slot, i, self._stage[k], bgr, bottom_up, (row0, rows))
                             self._freed[k].record(self._pre_stream)
                         self._issued += 1
                     else:
@@ -221,13 +260,15 @@ class PredictEngine:
 
     # -- end to end from pinned host memory --------------------------------------------------------------------------
     def submit_host(self, raws_host, masks_host=None, bgr=True, bottom_up=True, exclude_nodes=False, want_processed=False,
-                    only_preprocess=False):
+                    only_preprocess=False, spans=None):
         """Enqueue one batch of pinned u8 CPU tensors (raw pixel arrays) and return a ticket at once; at most two
         tickets may be outstanding.  ``collect`` waits for it.  want_processed: also copy the processed (resized +
-        trimmed) images back (``ticket.slot.proc_host[i, :rows[i]]`` after collect); only_preprocess: stop after K1."""
+        trimmed) images back (``ticket.slot.proc_host[i, :rows[i]]`` after collect); only_preprocess: stop after K1.
+        spans: optional list of (row0, rows) per scan from a producer that already knows the zero bands (e.g. the thread
+        that read the file); otherwise the engine scans."""
         n = len(raws_host)
         slot = self._run(n, lambda i: raws_host[i], masks_host, bgr, bottom_up, exclude_nodes, False, want_processed,
-                         only_preprocess)
+                         only_preprocess, spans)
         slot.pending = True
         return Ticket(slot, n, masks_host)
 

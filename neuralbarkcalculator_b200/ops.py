@@ -41,13 +41,41 @@ def _half(t, name):
 
 
 # ---- K1 -------------------------------------------------------------------------------------------------------
-def preprocess_4x(raw, H, W, pitch=None, bgr=False, bottom_up=False, workspace=None):
+def host_zero_row_span(raw_host, H, pitch, row_bytes=None, group=4):
+    """(row0, rows) of a HOST pixel array (u8 CPU tensor or numpy array, H rows of ``pitch`` bytes): the memory rows between
+    its all-zero bands, widened outwards to whole groups of ``group`` rows; rows = 0 for an all-zero image.  Host code in
+    the library (no GPU); ctypes releases the GIL."""
+    lib = _lib.load()
+    ptr = raw_host.data_ptr() if hasattr(raw_host, 'data_ptr') else raw_host.ctypes.data
+    r0, rows = C.c_int32(0), C.c_int32(0)
+    _lib.check(lib.nbc_host_zero_row_span(C.c_void_p(ptr), H, pitch, pitch if row_bytes is None else row_bytes, group,
+                                          C.byref(r0), C.byref(rows)), 'nbc_host_zero_row_span')
+    return r0.value, rows.value
+
+
+def preprocess_4x(raw, H, W, pitch=None, bgr=False, bottom_up=False, workspace=None, span=None):
     """raw: u8 CUDA tensor holding an H x W x 3 pixel array (row pitch ``pitch`` bytes).
     Returns (out u8 [(H/4)*(W/4)*3] flat buffer, first_last int32[2] CUDA tensor).
-    The trimmed image is ``out[:(last-first)*(W/4)*3].view(last-first, W/4, 3)``.  (models.py:191-203)"""
+    The trimmed image is ``out[:(last-first)*(W/4)*3].view(last-first, W/4, 3)``.  (models.py:191-203)
+    span = (row0, rows): ``raw`` holds only those memory rows (multiples of 4); the other rows of the H x W image are all
+    zero and never read (see ``host_zero_row_span``) -- same bytes out as for the full image."""
     lib = _lib.load()
     raw = _contig(raw, torch.uint8, 'raw')
     pitch = W * 3 if pitch is None else pitch
+    if span is not None:
+        with torch.cuda.device(raw.device):
+            need = lib.nbc_preprocess_workspace_bytes(H, W)
+            if workspace is None or workspace.numel() < need:
+                workspace = torch.empty(need, dtype=torch.uint8, device=raw.device)
+            out = torch.empty((H // 4) * (W // 4) * 3, dtype=torch.uint8, device=raw.device)
+            fl = torch.empty(2, dtype=torch.int32, device=raw.device)
+            if raw.numel() < span[1] * pitch - (pitch - W * 3):
+                raise RuntimeError('preprocess_4x: the span buffer holds fewer than %d rows' % span[1])
+            _lib.check(lib.nbc_preprocess_4x_span_u8(_ptr(raw) if span[1] else None, H, W, pitch,
+                                                     (1 if bgr else 0) | (2 if bottom_up else 0), span[0], span[1], _ptr(out),
+                                                     _ptr(fl), _ptr(workspace), workspace.numel(), _stream(raw.device)),
+                       'nbc_preprocess_4x_span_u8')
+        return out, fl
     with torch.cuda.device(raw.device):
         need = lib.nbc_preprocess_workspace_bytes(H, W)
         if workspace is None or workspace.numel() < need:

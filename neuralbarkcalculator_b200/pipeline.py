@@ -21,6 +21,7 @@ import numpy as np
 import torch
 from ._png import write_png
 from .dataset import make_dataset
+from . import ops
 from .engine import PredictEngine
 
 RAW = 4096
@@ -151,6 +152,7 @@ class FolderPipeline:
         n_tokens = min(3 * B, len(items))
         tokens = list(range(n_tokens))           # free tokens (main thread only)
         pinned = [None] * n_tokens
+        spans = [None] * n_tokens
         mask_sets = [[torch.empty((RAW // 4) * (RAW // 4), dtype=torch.uint8).pin_memory() for _ in range(min(B, len(items)))]
                      for _ in range(2)]
         rows_csv = [None] * len(items)
@@ -165,6 +167,8 @@ class FolderPipeline:
                 pinned[tok] = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
             t0 = time.perf_counter()
             self._read_into(items[i][0], geo[i][0], pinned[tok])
+            # the reader knows the scan best while it is cache-hot: the all-zero dark bands stay on the host (engine.py)
+            spans[tok] = ops.host_zero_row_span(pinned[tok], RAW, RAW * 3) if self.engine.zero_span else (0, RAW)
             timing['read_s'] += time.perf_counter() - t0
             return tok
 
@@ -211,7 +215,7 @@ class FolderPipeline:
                 toks = [loads[i].result() for i in idx]
                 ticket = self.engine.submit_host([pinned[t] for t in toks], None if only_preprocess else mask_sets[(a // B) & 1][:len(idx)],
                                                  bgr=True, bottom_up=bottom_up, exclude_nodes=excludes_nodes, want_processed=True,
-                                                 only_preprocess=only_preprocess)
+                                                 only_preprocess=only_preprocess, spans=[spans[t] for t in toks])
                 pending.append((ticket, idx, toks))
                 if len(pending) == 2:
                     finish(pending.pop(0))

@@ -82,6 +82,45 @@ def test_preprocess_full_size_and_edges(cuda_device):
     assert (first, last) == (0, 16) and np.array_equal(out, expect)
 
 
+def test_preprocess_zero_band_span(cuda_device):
+    """Dark bands that never cross PCIe: the host scan finds the all-zero rows above / below the content, only the span in
+    between is given to K1 (nbc_preprocess_4x_span_u8) and the result -- resized bytes, [first, last), the global
+    min / max clip -- is bit-identical to K1 on the whole scan."""
+    ops = _ops()
+    cases = []
+    raw, _, _ = synth.raw_image_u8(seed=11, size=1024, top=203, bottom=118)          # bands that are not multiples of 4
+    cases.append(('bands', raw))
+    r2 = raw.copy()
+    r2[37, 500, 1] = 9                                                               # a stray byte inside the top band
+    r2[1024 - 5, 3, 2] = 1                                                           # ... and near the bottom edge
+    cases.append(('stray bytes', r2))
+    r3 = np.clip(synth.texture_u8(512, 512, 12), 30, 220).astype(np.uint8)           # no zero anywhere: min = 30 clips
+    cases.append(('no bands', r3))
+    r4 = r3.copy()
+    r4[:64] = 0                                                                      # zero band => global min 0 although
+    cases.append(('band changes the clip', r4))                                      # the copied rows have min 30
+    cases.append(('all zero', np.zeros((256, 256, 3), np.uint8)))
+    for name, img in cases:
+        for bgr, bottom_up in ((False, False), (True, True)):
+            H, W, _ = img.shape
+            src = img[:, :, ::-1] if bgr else img
+            src = np.ascontiguousarray(src[::-1] if bottom_up else src)
+            row0, rows = ops.host_zero_row_span(src, H, W * 3)
+            nz = np.flatnonzero(src.reshape(H, -1).any(axis=1))
+            if len(nz):
+                assert row0 == nz[0] // 4 * 4 and row0 + rows == min(H, -(-(nz[-1] + 1) // 4) * 4), name
+            else:
+                assert rows == 0
+            full = torch.from_numpy(src).to(cuda_device).view(-1)
+            a, fla = ops.preprocess_4x(full, H, W, bgr=bgr, bottom_up=bottom_up)
+            part = torch.from_numpy(src[row0:row0 + rows].copy()).to(cuda_device).view(-1)
+            b, flb = ops.preprocess_4x(part, H, W, bgr=bgr, bottom_up=bottom_up, span=(row0, rows))
+            assert fla.tolist() == flb.tolist(), name
+            n = (fla[1] - fla[0]).item() * (W // 4) * 3
+            assert torch.equal(a[:n], b[:n]), name
+    assert rows == 0       # the last case really was the empty span
+
+
 def test_preprocess_general_ratio(cuda_device):
     """Any size -> target x target (models.py:194-198) against the f64 restatement, byte for byte: non-integer ratios both
     ways, upscaling of one axis, BGR / bottom-up sources, dark bands that trigger the trim, an input range that clips."""
@@ -324,8 +363,6 @@ def test_stem_maxpool_head(cuda_device):
     assert (lg - refl).abs().max() < 1e-4
 
 
-@pytest.mark.skipif(os.environ.get('NBC_TEST_EXPERIMENTAL', '0') != '1' or os.environ.get('NBC_STEM_HALO', '0') != '1',
-                    reason='stem halo kernel: built in round 1, not yet verified on a GPU (NBC_TEST_EXPERIMENTAL=1 NBC_STEM_HALO=1 runs it)')
 def test_stem_halo_kernel(cuda_device):
     """conv_tc_stem_kernel (overlapping no-swizzle windows out of a 7-row halo) at the production tile geometry (128 x 1
     output tiles): full-width rows, a width that leaves a partial last tile, a batch, fp16 storage."""

@@ -281,3 +281,60 @@ def test_profile_tools_read_the_committed_launch_list():
     assert int(rows['conv_tc_pair_kernel'][1]) + int(rows['conv_tc_kernel'][1]) == 100
     assert abs(sum(float(r[-2]) for r in rows.values()) - 100.0) < 0.5
     assert 'total' in out and '176 launches' in out
+
+
+def test_integration_doc_calls_match_the_abi():
+    """Every `_nbc.nbc_*(...)` call in INTEGRATION.md's binding snippets passes as many arguments as the C-ABI takes
+    (`_lib.SIGNATURES`, itself cross-checked against include/nbc.h above) -- a maintainer who copies the snippet must not
+    end up passing garbage as a trailing argument."""
+    import re
+    from neuralbarkcalculator_b200 import _lib
+    text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    calls = 0
+    for m in re.finditer(r'_nbc\.(nbc_\w+)\(', text):
+        name = m.group(1)
+        assert name in _lib.SIGNATURES, 'INTEGRATION.md calls %s, which the ABI does not export' % name
+        depth, i, nargs, seen = 1, m.end(), 0, False
+        while depth:
+            ch = text[i]
+            if ch in '([{':
+                depth += 1
+            elif ch in ')]}':
+                depth -= 1
+            elif ch == ',' and depth == 1:
+                nargs += 1
+            elif ch == '#':                      # a comment inside a multi-line call
+                i = text.index('\n', i)
+                continue
+            if depth and not ch.isspace():
+                seen = True
+            i += 1
+        nargs += 1 if seen else 0
+        assert nargs == len(_lib.SIGNATURES[name][1]), '%s: INTEGRATION.md passes %d arguments, the ABI takes %d' % (
+            name, nargs, len(_lib.SIGNATURES[name][1]))
+        calls += 1
+    assert calls >= 5
+
+
+def test_host_zero_row_span():
+    """nbc_host_zero_row_span (host code of the library): first / last non-zero memory row, widened to groups of 4."""
+    from neuralbarkcalculator_b200 import ops
+    H, pitch = 64, 100
+    a = np.zeros((H, pitch), np.uint8)
+    assert ops.host_zero_row_span(a, H, pitch) == (0, 0)
+    a[13, 99] = 1
+    assert ops.host_zero_row_span(a, H, pitch) == (12, 4)
+    a[13, 99] = 0
+    a[13, 97] = 1                                   # beyond row_bytes: padding is not image data
+    assert ops.host_zero_row_span(a, H, pitch, row_bytes=96) == (0, 0)
+    a[40, 0] = 7
+    assert ops.host_zero_row_span(a, H, pitch) == (12, 32)
+    a[63, 5] = 1
+    a[0, 1] = 1
+    assert ops.host_zero_row_span(a, H, pitch) == (0, 64)
+    b = np.zeros((10, 8), np.uint8)                 # H not a multiple of the group: the span is clipped to the image
+    b[9, 0] = 1
+    assert ops.host_zero_row_span(b, 10, 8) == (8, 2)
+    t = torch.zeros(32 * 24, dtype=torch.uint8)
+    t[5 * 24 + 3] = 1
+    assert ops.host_zero_row_span(t, 32, 24) == (4, 4)
