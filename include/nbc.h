@@ -244,6 +244,15 @@ int nbc_train_forward_backward(nbc_train_plan* plan, float* params, float* stats
                                int input_kind, const float* mean3_host, const float* std3_host, const uint8_t* target,
                                const float* weights3, float dropout_p, uint64_t seed, float* loss, void* workspace,
                                size_t workspace_bytes, void* stream);
+/* Gradient-ready events, for overlapping the data-parallel all-reduce with the backward.  The flat
+ * gradient buffer becomes final in SEGMENTS, last layer first: segment 0 = head conv + classifier, then the 16 bottleneck
+ * blocks last to first, then the stem.  nbc_train_segment gives segment i's range (in floats);
+ * nbc_train_wait_segment makes `stream` wait (cudaStreamWaitEvent) until segment i of the most recently enqueued
+ * nbc_train_forward_backward is final -- the caller then all-reduces that range on `stream` while the backward of the
+ * earlier layers is still running. */
+int nbc_train_num_segments(const nbc_train_plan* plan);
+int nbc_train_segment(const nbc_train_plan* plan, int i, int64_t* offset, int64_t* count);
+int nbc_train_wait_segment(nbc_train_plan* plan, int i, void* stream);
 /* test / debug accessors: workspace byte offset + {N,H,W,C} of an intermediate (what: 0 z of unit, 1 y of unit,
  * 2 low-res logits, 3 full-res logits, 4 dL/dfull, 5 dL/dlow); units are in state_dict order (0 = stem). */
 int64_t nbc_train_debug_offset(const nbc_train_plan* plan, int what, int index, int32_t* dims_out);

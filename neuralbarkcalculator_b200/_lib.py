@@ -78,6 +78,9 @@ SIGNATURES = {
     'nbc_train_forward_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, C.POINTER(c_float),
                                    C.POINTER(c_float), c_void_p, c_void_p, c_float, C.c_uint64, c_void_p, c_void_p, c_size_t,
                                    c_void_p]),
+    'nbc_train_num_segments': (c_int, [c_void_p]),
+    'nbc_train_segment': (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    'nbc_train_wait_segment': (c_int, [c_void_p, c_int, c_void_p]),
     'nbc_train_debug_offset': (c_i64, [c_void_p, c_int, c_int, C.POINTER(C.c_int32)]),
     'nbc_train_num_units': (c_int, [c_void_p]),
     'nbc_train_set_wgrad_impl': (c_int, [c_void_p, c_int]),

@@ -51,6 +51,12 @@ struct nbc_train_plan {
   int wgrad_impl = 0;   // 0 = tcgen05 (wgrad_tc.cu), 1 = mma.sync / CUDA-core cross-check kernels
   int loss_kind = 0;    // 0 = weighted CE, 1 = Lovasz-Softmax, 2 = CE / 4 + Lovasz
   size_t lov_off = 0, dfull2_off = 0, loss2_off = 0;
+  // gradient-ready events, one per SEGMENT of the flat gradient buffer in the order the backward finishes them:
+  // segment 0 = head conv + classifier, then the bottleneck blocks last to first, then the stem (created lazily)
+  std::vector<cudaEvent_t> seg_events;
+  ~nbc_train_plan() {
+    for (cudaEvent_t e : seg_events) cudaEventDestroy(e);
+  }
 };
 
 namespace nbc {
@@ -197,6 +203,42 @@ extern "C" nbc_train_plan* nbc_train_create(int N, int H, int W) {
 }
 
 extern "C" void nbc_train_destroy(nbc_train_plan* p) { delete p; }
+
+// ---- gradient segments (for overlapping the data-parallel all-reduce with the backward) ------------------------------
+extern "C" int nbc_train_num_segments(const nbc_train_plan* p) { return p ? (int)p->blocks.size() + 2 : 0; }
+
+extern "C" int nbc_train_segment(const nbc_train_plan* p, int i, int64_t* offset, int64_t* count) {
+  NBC_REQUIRE(p && offset && count && i >= 0 && i < (int)p->blocks.size() + 2, "nbc_train_segment: bad argument");
+  const int nb = (int)p->blocks.size();
+  size_t lo, hi;
+  if (i == 0) {
+    lo = p->units[p->head_unit].w_off, hi = p->n_params;
+  } else if (i <= nb) {
+    const int b = nb - i;      // blocks last to first
+    lo = p->units[p->blocks[b].c1].w_off;
+    hi = (b + 1 < nb) ? p->units[p->blocks[b + 1].c1].w_off : p->units[p->head_unit].w_off;
+  } else {
+    lo = 0, hi = p->units[p->blocks[0].c1].w_off;      // the stem
+  }
+  *offset = (int64_t)lo, *count = (int64_t)(hi - lo);
+  return 0;
+}
+
+static int record_segment(nbc_train_plan* p, int i, cudaStream_t stream) {
+  if (p->seg_events.empty()) {
+    p->seg_events.resize(p->blocks.size() + 2);
+    for (cudaEvent_t& e : p->seg_events) NBC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  NBC_CUDA(cudaEventRecord(p->seg_events[i], stream));
+  return 0;
+}
+
+extern "C" int nbc_train_wait_segment(nbc_train_plan* p, int i, void* stream) {
+  NBC_REQUIRE(p && i >= 0 && i < (int)p->blocks.size() + 2, "nbc_train_wait_segment: bad argument");
+  NBC_REQUIRE(!p->seg_events.empty(), "nbc_train_wait_segment: no backward has been enqueued yet");
+  NBC_CUDA(cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(stream), p->seg_events[i], 0));
+  return 0;
+}
 extern "C" int64_t nbc_train_param_count(const nbc_train_plan* p) { return p ? (int64_t)p->n_params : 0; }
 extern "C" int64_t nbc_train_stats_count(const nbc_train_plan* p) { return p ? (int64_t)p->n_stats : 0; }
 extern "C" size_t nbc_train_workspace_bytes(const nbc_train_plan* p) { return p ? p->ws_bytes : 0; }
@@ -414,7 +456,9 @@ extern "C" int nbc_train_forward_backward(nbc_train_plan* p, float* params, floa
                          grads + p->cls_w_off, grads + p->cls_b_off, stream)))
     return rc;
   if ((rc = unit_backward(c, head, ws + p->d2_off, 1, nullptr))) return rc;
-  for (int b = (int)p->blocks.size() - 1; b >= 0; --b) {
+  if ((rc = record_segment(p, 0, stream))) return rc;
+  const int nb = (int)p->blocks.size();
+  for (int b = nb - 1; b >= 0; --b) {
     TBlock& B = p->blocks[b];
     Unit &u1 = p->units[B.c1], &u2 = p->units[B.c2], &u3 = p->units[B.c3];
     // y3 = relu(bn3(z3) + skip): masked gradient g3 feeds both the main path and the skip path (kept in gskip)
@@ -426,12 +470,13 @@ extern "C" int nbc_train_forward_backward(nbc_train_plan* p, float* params, floa
     }
     // conv1's data gradient + skip gradient = gradient w.r.t. the block input
     if ((rc = unit_backward(c, u1, ws + p->d1_off, 1, nullptr))) return rc;
+    if ((rc = record_segment(p, nb - b, stream))) return rc;
   }
   // maxpool and stem
   const size_t g_pool = p->blocks[0].gout_off;
   if ((rc = maxpool_backward(ws + g_pool, ws + p->pidx_off, N, p->H2, p->W2, 64, ws + p->gskip_off, stream))) return rc;
   if ((rc = unit_backward(c, stem, ws + p->gskip_off, 1, nullptr))) return rc;
-  return 0;
+  return record_segment(p, nb + 1, stream);
 }
 
 // debug / test accessor: byte offset into the workspace and geometry of an intermediate tensor.

@@ -6,6 +6,7 @@ Changed: samples are handed over as **uint8 HWC arrays** (no ToTensor float conv
 Normalize of dataset.py:181-190 + models.py:233-237 happen inside the CUDA stem kernel), and a 24-bit BMP is not
 decoded at all: its bottom-up BGR pixel array is passed to the resize kernel as is."""
 import os
+import random
 import struct
 
 import numpy as np
@@ -78,9 +79,14 @@ def read_bmp_pixels(path):
 class RegressionDatasetFolder:
     """Index-able folder dataset with the reference's constructor arguments (dataset.py:93-149).
 
-    ``__getitem__`` returns ``(sample_u8_hwc, target_u8_or_None, fname, wood_type)`` when ``include_fname`` else
-    ``(sample, target)``; transforms, if given, are applied as in dataset.py:175-190 (transform, then
-    input_only_transform)."""
+    Without transforms ``__getitem__`` hands out what the GPU path consumes: ``(sample_u8_hwc, target_u8_or_None[, fname,
+    wood_type])`` -- raw uint8 arrays; /255, Normalize and the label rounding happen in the CUDA kernels
+    (``augment.augment_batch`` is the native training loader).  With transforms it behaves as dataset.py:162-205: ONE random
+    draw shared by image and label (the generators -- python ``random``, as the reference seeds, and torch's, which current
+    torchvision transforms draw from -- are re-seeded with the same number before each of the two ``transform`` calls, so
+    a RandomCrop / flip cuts both identically), then ``input_only_transform`` on the image, then, when the transforms
+    produced tensors (``ToTensor``), the reference's label conversion: /255 if max > 200, ``round(target * 2)`` as a long
+    class map, and a zero map of the image's size when the image has no dual."""
 
     def __init__(self, root, extensions=IMG_EXTENSIONS, loader=pil_loader, transform=None, input_only_transform=None,
                  include_fname=False, in_memory=False):
@@ -105,11 +111,29 @@ class RegressionDatasetFolder:
             sample = self.loader(sample)
             target = self.loader(target, grayscale=True) if target else None
         if self.transform is not None:
+            import torch
+            random_seed = np.random.randint(2147483647)
+            random.seed(random_seed)
+            torch.manual_seed(random_seed)
             sample = self.transform(sample)
             if target is not None:
+                random.seed(random_seed)
+                torch.manual_seed(random_seed)
                 target = self.transform(target)
         if self.input_only_transform is not None:
             sample = self.input_only_transform(sample)
+        if (self.transform is not None or self.input_only_transform is not None) and hasattr(sample, 'dim'):
+            import torch                                   # tensors: the reference's conversions, dataset.py:192-203
+            if target is not None:
+                target = target if hasattr(target, 'dim') else torch.as_tensor(np.asarray(target))
+                target = target.float()
+                if target.max() > 200:
+                    target = target / 255
+                if sample.max() > 200:
+                    sample = sample / 255
+                target = (target * 2).round_().long().squeeze()
+            else:
+                target = torch.zeros(sample.shape[1], sample.shape[2])
         if self.include_fname:
             return sample, target, fname, wood_type
         return sample, target

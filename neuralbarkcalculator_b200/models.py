@@ -53,12 +53,28 @@ class SimpleSegmentationModel(nn.Module):
         self._precision = DEFAULT_PRECISION
 
     # -- native plan management ------------------------------------------------------------------------------
+    # The plan holds BN-folded 16-bit copies of the weights, so it must be rebuilt when they change.  Everything that
+    # replaces or moves parameters through the nn.Module API invalidates it (load_state_dict, .to / .cuda / .half / .float
+    # via _apply); the per-call check is O(1) -- two sentinel tensors' (data_ptr, version).  In-place edits that bypass
+    # the version counter (``p.data.copy_()``) need an explicit ``invalidate_plan()``.
+    def invalidate_plan(self):
+        self._plan = None
+        self._plan_key = None
+
+    def load_state_dict(self, *args, **kwargs):
+        self.invalidate_plan()
+        return super().load_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate_plan()
+        return super()._apply(fn, *args, **kwargs)
+
     def _state_key(self):
-        sd = self.state_dict(keep_vars=True)
-        return tuple((t.data_ptr(), t._version) for t in sd.values())
+        first, last = self.backbone.conv1.weight, self.classifier[4].bias
+        return (first.data_ptr(), first._version, last.data_ptr(), last._version)
 
     def native_plan(self):
-        """Build (or reuse) the nbc_plan holding BN-folded bf16 weights for the current parameters."""
+        """Build (or reuse) the nbc_plan holding the BN-folded 16-bit weights for the current parameters."""
         key = self._state_key()
         if self._plan is None or key != self._plan_key:
             sd = self.state_dict(keep_vars=True)

@@ -4,9 +4,14 @@
 step in ``libnbc.so``: train-mode forward (batch-statistics BatchNorm, Dropout(0.8) in the head as
 ``fcn_resnet50(dropout=0.8)``), ``CustomWeightedCrossEntropy`` (utils.py:151-165), full backward, and Adam
 (lr 5e-4, L2 weight decay 2e-3 as ``__main__.py:234``).  Data parallel: one process per GPU, the flat gradient buffer is
-all-reduced over NCCL (``torch.distributed``) between backward and the optimiser -- the only collective of the path.
+all-reduced over NCCL (``torch.distributed``) between backward and the optimiser -- the only collective of the path --
+in BUCKETS that start while the backward is still running: the native backward records an event each time a segment of
+the gradient buffer (head, then the bottleneck blocks last to first, then the stem) is final, consecutive segments are
+merged into buckets of >= ``bucket_mb`` and each bucket's all-reduce is enqueued on a side stream behind its event
+(``NBC_TRAIN_BUCKETS=0`` or ``bucket_mb=0``: one all-reduce after the backward).  Adam waits for all of them.
 No torch autograd, no torch ops on the data path."""
 import ctypes as C
+import os
 
 import torch
 
@@ -14,10 +19,37 @@ from . import _lib, ops
 from .utils import get_pos_weight
 
 
+def gradient_segments(lib, handle):
+    """[(offset, count)] of the flat gradient buffer in the order the native backward finishes them (head + classifier, the
+    bottleneck blocks last to first, the stem); needs no GPU."""
+    h = C.c_void_p(handle)
+    out = []
+    for i in range(lib.nbc_train_num_segments(h)):
+        off, cnt = C.c_int64(0), C.c_int64(0)
+        _lib.check(lib.nbc_train_segment(h, i, C.byref(off), C.byref(cnt)), 'nbc_train_segment')
+        out.append((off.value, cnt.value))
+    return out
+
+
+def merge_segments(segments, min_bytes):
+    """Consecutive segments (contiguous in memory, descending) merged until a bucket holds at least ``min_bytes`` of f32
+    gradients -> [(index of the bucket's last segment, offset, count)]."""
+    out, lo, hi = [], None, None
+    for i, (off, cnt) in enumerate(segments):
+        a, b = off, off + cnt
+        if hi is not None and b != lo:
+            raise RuntimeError('gradient segments must be contiguous, last layer first')
+        lo, hi = a, (b if hi is None else hi)
+        if (hi - lo) * 4 >= min_bytes or i == len(segments) - 1:
+            out.append((i, lo, hi - lo))
+            hi = None
+    return out
+
+
 class Trainer:
     def __init__(self, state_dict, N, H, W, device='cuda:0', lr=5e-4, weight_decay=2e-3, betas=(0.9, 0.999), eps=1e-8,
                  dropout=0.8, class_weights=None, mean=(0.7399, 0.6139, 0.4401), std=(0.1068, 0.1272, 0.1271),
-                 loss='weighted_ce'):
+                 loss='weighted_ce', bucket_mb=16.0, seed=0):
         self.lib = _lib.load()
         self.device = torch.device(device)
         _lib.require_device(self.device.index if self.device.index is not None else torch.cuda.current_device())
@@ -26,6 +58,12 @@ class Trainer:
         self.mean3 = (C.c_float * 3)(*mean)
         self.std3 = (C.c_float * 3)(*std)
         self.step_count = 0
+        self.base_seed = int(seed)
+        if os.environ.get('NBC_TRAIN_BUCKETS', '1') == '0':
+            bucket_mb = 0.0
+        self.bucket_mb = float(bucket_mb)
+        self._buckets = None
+        self._comm_stream = None
         self.keys = list(state_dict.keys())
         if len(self.keys) != 326:
             raise RuntimeError('Trainer expects the 326-key fcn_resnet50 state_dict')
@@ -144,12 +182,43 @@ class Trainer:
                 self.num_batches_tracked[k] += 1
         return self.loss
 
+    def gradient_buckets(self):
+        """[(last segment of the bucket, offset, count)] in the order the backward completes them: consecutive gradient
+        segments (``nbc_train_segment``) merged until a bucket holds at least ``bucket_mb`` MB."""
+        if self._buckets is None:
+            self._buckets = merge_segments(gradient_segments(self.lib, self.handle), self.bucket_mb * 1e6)
+            assert sum(c for _, _, c in self._buckets) == self.grads.numel()
+        return self._buckets
+
+    def all_reduce_gradients(self):
+        """SUM the gradients over the data-parallel group (Adam applies 1/world).  Bucketed: every bucket's all-reduce is
+        enqueued on a side stream behind the event the backward records when that part of the buffer is final, so the
+        exchange of the last layers runs under the backward of the first ones.  Returns the number of collectives."""
+        import torch.distributed as dist
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if world == 1:
+            return 0
+        if self.bucket_mb <= 0:
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
+            return 1
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(self.device)
+        works = []
+        with torch.cuda.device(self.device):
+            for seg, off, cnt in self.gradient_buckets():
+                _lib.check(self.lib.nbc_train_wait_segment(C.c_void_p(self.handle), seg, C.c_void_p(self._comm_stream.cuda_stream)),
+                           'nbc_train_wait_segment')
+                with torch.cuda.stream(self._comm_stream):
+                    works.append(dist.all_reduce(self.grads[off:off + cnt], op=dist.ReduceOp.SUM, async_op=True))
+            for w in works:
+                w.wait()          # the current stream (Adam's) waits for the collective; the host does not block
+        return len(works)
+
     def optimizer_step(self):
         """All-reduce the gradients over the data-parallel group (if any), then one fused Adam pass."""
         import torch.distributed as dist
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        if world > 1:
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
+        self.all_reduce_gradients()
         self.step_count += 1
         with torch.cuda.device(self.device):
             _lib.check(self.lib.nbc_train_adam(C.c_void_p(self.params.data_ptr()), C.c_void_p(self.grads.data_ptr()),
@@ -159,7 +228,14 @@ class Trainer:
                                                C.c_float(1.0 / world),
                                                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), 'nbc_train_adam')
 
+    def dropout_seed(self):
+        """A different dropout mask per step, per data-parallel rank and per run seed (every rank drawing the same mask
+        would correlate the replicas' gradients)."""
+        import torch.distributed as dist
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        return (self.base_seed << 40) + (rank << 28) + self.step_count
+
     def step(self, images, targets, seed=None):
-        loss = self.forward_backward(images, targets, seed=self.step_count if seed is None else seed)
+        loss = self.forward_backward(images, targets, seed=self.dropout_seed() if seed is None else seed)
         self.optimizer_step()
         return loss

@@ -1,6 +1,7 @@
 """Host-side mirror of the hot-path pieces of the reference's ``utils.py``: ``remove_small_zones`` (utils.py:135-148),
-``CustomWeightedCrossEntropy`` (utils.py:151-165) and ``get_pos_weight`` (utils.py:72-73).  Same names, arguments
-and in-place behaviour; the work is done by the CUDA kernels behind ``libnbc.so``."""
+``CustomWeightedCrossEntropy`` (utils.py:151-165), ``get_pos_weight`` (utils.py:72-73), the metrics, and the training
+loader's index bookkeeping (``get_splits``, utils.py:76-132; the weighted epoch sampler of ``__main__.py:165-172``).  Same
+names, arguments and in-place behaviour; the pixel work is done by the CUDA kernels behind ``libnbc.so``."""
 import torch
 from torch import nn
 
@@ -13,6 +14,70 @@ from .lovasz_losses import LovaszSoftmax
 def get_pos_weight():
     """utils.py:72-73."""
     return torch.FloatTensor([0.4004, 2.0334, 93.1921])
+
+
+_WOOD_TYPE_TO_IDX = {'epinette_gelee': 0, 'epinette_non_gelee': 1, 'sapin': 2}     # utils.py:83-87
+
+
+def get_splits(dataset, label_pixels=None):
+    """utils.py:76-132: per-wood-type 80 / 10 / 10 split (``ceil`` / ``floor``, each type shuffled with numpy's global
+    generator in the fixed type order) and the sampling weights of the training items,
+    ``exp(wood_type_weight * labelled_pixels / sum(labelled_pixels))`` normalised over the training split, in the
+    reference's float32 arithmetic.  Returns (train_split, valid_split, test_split, train_weights) as numpy arrays.
+
+    ``dataset`` yields ``(_, target, _, wood_type)`` like ``RegressionDatasetFolder(include_fname=True)``; targets may be
+    class maps (torch / numpy).  ``label_pixels`` (optional, one number per item: how many pixels are not class 0) skips
+    the scan of the targets -- the native loader counts them on the GPU."""
+    from math import ceil, floor
+    total_items = len(dataset)
+    idxs_by_type = [[] for _ in range(3)]
+    sample_weight = []
+    wood_types = []
+    for i, item in enumerate(dataset):
+        target, wood_type = item[1], item[3]
+        wood_types.append(wood_type)
+        idxs_by_type[_WOOD_TYPE_TO_IDX[wood_type]].append(i)
+        if label_pixels is not None:
+            sample_weight.append(float(label_pixels[i]))
+        else:
+            t = torch.as_tensor(np.asarray(target) if not isinstance(target, torch.Tensor) else target)
+            sample_weight.append(float(t.numel() - int((t == 0).sum())))
+    sample_weight = torch.tensor(sample_weight)                    # float32, as the reference's tensor of python floats
+    sample_weight = sample_weight / sample_weight.sum()
+    train_split, valid_split, test_split = [], [], []
+    wood_type_weights = []
+    for k in range(3):
+        idxs = np.asarray(idxs_by_type[k])
+        np.random.shuffle(idxs)
+        n_data = len(idxs)
+        wood_type_weights.append(total_items / (3 * n_data))
+        n_train = int(ceil(0.8 * n_data))
+        n_valid = int(floor(0.1 * n_data))
+        train_split.extend(idxs[:n_train])
+        valid_split.extend(idxs[n_train:n_train + n_valid])
+        test_split.extend(idxs[n_train + n_valid:])
+    wood_type_weights = np.asarray(wood_type_weights)
+    wood_type_weights /= wood_type_weights.sum()
+    train_weights = torch.zeros(total_items).float()
+    for i, wood_type in enumerate(wood_types):                     # float64 scalar x float32 tensor element, stored as float32
+        train_weights[i] = wood_type_weights[_WOOD_TYPE_TO_IDX[wood_type]] * sample_weight[i]
+    train_split, valid_split, test_split = np.asarray(train_split), np.asarray(valid_split), np.asarray(test_split)
+    train_weights = np.exp(np.asarray(train_weights))
+    train_weights = train_weights[train_split]
+    train_weights /= train_weights.sum()
+    return train_split, valid_split, test_split, train_weights
+
+
+def weighted_epoch_batches(train_split, train_weights, batch_size, samples_per_item=12, generator=None):
+    """The batches of one training epoch as dataset indices, as ``__main__.py:165-172`` draws them:
+    ``BatchSampler(WeightedRandomSampler(train_weights, len(train_weights) * 12, replacement=True), batch_size,
+    drop_last=True)`` over ``Subset(dataset, train_split)`` -- one ``torch.multinomial`` draw, cut into full batches.
+    Returns int64 [n_batches, batch_size]; feed a row to ``augment.augment_batch`` (the native loader)."""
+    w = torch.as_tensor(np.asarray(train_weights), dtype=torch.double)
+    draws = torch.multinomial(w, len(w) * samples_per_item, True, generator=generator)
+    n_batches = len(draws) // batch_size
+    idx = torch.as_tensor(np.asarray(train_split), dtype=torch.int64)[draws[:n_batches * batch_size]]
+    return idx.view(n_batches, batch_size)
 
 
 def remove_small_zones(img, threshold=150):

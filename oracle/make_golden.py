@@ -228,6 +228,25 @@ def main():
     np.savez_compressed(os.path.join(OUT, 'ccl_small.npz'), mask=m.astype(np.uint8), out=a.astype(np.uint8),
                         unpinned=np.array('restates scikit-image 0.15 remove_small_holes/objects'))
 
+    # ---- training loader bookkeeping (N4): the reference's own get_splits + torch's weighted batch sampler ---------------
+    rng = np.random.default_rng(3)
+    woods = ['epinette_gelee'] * 13 + ['epinette_non_gelee'] * 17 + ['sapin'] * 7
+    fake = []
+    for i, w in enumerate(woods):
+        t = torch.from_numpy((rng.random((24, 32)) < rng.uniform(0.05, 0.6)).astype(np.int64) * rng.integers(1, 3, (24, 32)))
+        fake.append((None, t, 'img%d.png' % i, w))
+    np.random.seed(7)
+    tr, va, te, tw = ref_utils.get_splits(fake)
+    from torch.utils.data import BatchSampler, WeightedRandomSampler
+    gen = torch.Generator().manual_seed(5)
+    batches = list(BatchSampler(WeightedRandomSampler(tw, num_samples=len(tw) * 12, replacement=True, generator=gen),
+                                batch_size=5, drop_last=True))                                    # __main__.py:165-168
+    np.savez_compressed(os.path.join(OUT, 'splits_small.npz'), woods=np.array(woods), seed=7, sampler_seed=5,
+                        label_pixels=np.array([int((t != 0).sum()) for _, t, _, _ in fake]), targets=np.stack([t.numpy() for _, t, _, _ in fake]).astype(np.uint8),
+                        train=tr, valid=va, test=te, weights=tw, batches=tr[np.asarray(batches)])
+    report.append('get_splits / weighted epoch sampler: fixture written by reference utils.get_splits and torch BatchSampler('
+                  'WeightedRandomSampler) (%d / %d / %d items, %d batches of 5)' % (len(tr), len(va), len(te), len(batches)))
+
     open(os.path.join(OUT, 'PINNING.txt'), 'w').write('\n'.join(report) + '\n')
     print('\n'.join(report))
 

@@ -338,3 +338,47 @@ def test_host_zero_row_span():
     t = torch.zeros(32 * 24, dtype=torch.uint8)
     t[5 * 24 + 3] = 1
     assert ops.host_zero_row_span(t, 32, 24) == (4, 4)
+
+
+def test_dataset_transforms_share_one_random_draw(tmp_path):
+    """RegressionDatasetFolder with transforms (dataset.py:162-205): image and label get the SAME random crop / flip, the
+    label becomes round(2 * gray / 255) as a long class map, and an image without a dual gets a zero map."""
+    from PIL import Image
+    import torchvision.transforms as T
+    from neuralbarkcalculator_b200.dataset import RegressionDatasetFolder
+    root = tmp_path / 'ds'
+    for sub in ('samples/sapin', 'duals/sapin'):
+        os.makedirs(root / sub)
+    rng = np.random.default_rng(0)
+    lab = rng.integers(0, 3, (40, 56)).astype(np.uint8)
+    img = np.stack([lab * 100, lab * 100 + 1, lab * 100 + 2], axis=-1).astype(np.uint8)      # the image encodes its label
+    Image.fromarray(img).save(root / 'samples/sapin/a.png')
+    Image.fromarray((lab * 127 + (lab == 2)).astype(np.uint8)).save(root / 'duals/sapin/a.png')   # 0 / 127 / 255
+    Image.fromarray(img).save(root / 'samples/sapin/b.png')                                   # no dual
+    tf = T.Compose([T.ToPILImage(), T.RandomCrop(24), T.RandomHorizontalFlip(), T.RandomVerticalFlip(), T.ToTensor()])
+    ds = RegressionDatasetFolder(str(root), transform=tf, include_fname=True)
+    for _ in range(8):
+        x, y, fname, wood = ds[0]
+        assert x.shape == (3, 24, 24) and y.shape == (24, 24) and y.dtype == torch.int64 and (fname, wood) == ('a.png', 'sapin')
+        assert torch.equal((x[0] * 255).round().long() // 100, y), 'image and label were cut differently'
+    x, y, _, _ = ds[1]
+    assert y.shape == (24, 24) and not y.any()
+    raw = RegressionDatasetFolder(str(root))[0]
+    assert raw[0].dtype == np.uint8 and raw[0].shape == (40, 56, 3) and raw[1].shape == (40, 56)
+
+
+def test_get_splits_and_epoch_sampler_match_reference(golden_dir):
+    """N4 bookkeeping: get_splits (utils.py:76-132) and the weighted epoch batches (__main__.py:165-172) against a fixture
+    written by the reference's own get_splits and torch's BatchSampler(WeightedRandomSampler) (oracle/make_golden.py)."""
+    from neuralbarkcalculator_b200 import utils as nu
+    g = np.load(os.path.join(golden_dir, 'splits_small.npz'))
+    ds = [(None, torch.from_numpy(t.astype(np.int64)), 'img%d.png' % i, str(w)) for i, (t, w) in enumerate(zip(g['targets'], g['woods']))]
+    np.random.seed(int(g['seed']))
+    tr, va, te, tw = nu.get_splits(ds)
+    assert np.array_equal(tr, g['train']) and np.array_equal(va, g['valid']) and np.array_equal(te, g['test'])
+    assert tw.dtype == np.float32 and np.array_equal(tw, g['weights'])                       # bit for bit
+    np.random.seed(int(g['seed']))
+    tr2, _, _, tw2 = nu.get_splits(ds, label_pixels=g['label_pixels'])                      # counts from the GPU loader
+    assert np.array_equal(tr2, tr) and np.array_equal(tw2, tw)
+    b = nu.weighted_epoch_batches(tr, tw, 5, generator=torch.Generator().manual_seed(int(g['sampler_seed'])))
+    assert np.array_equal(b.numpy(), g['batches'])
