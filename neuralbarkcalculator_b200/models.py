@@ -211,8 +211,10 @@ class Preprocessor():
 
 class NeuralBarkCalculator():
     """models.py:206-364: loads the checkpoint and writes ``results/outputs/<wood>/*.png`` and
-    ``results/final_stats.csv`` for every processed image.  (The matplotlib "combined image" of models.py:280-347 is
-    host-side plotting, out of scope for the hot path: written only when matplotlib is importable.)"""
+    ``results/final_stats.csv`` for every processed image, plus ``results/combined_images/<wood>/*.png`` as NBC_COMBINED says
+    (figure.py: the native two-panel stand-in by default, the reference's matplotlib figure of models.py:280-347 with
+    NBC_COMBINED=figure when matplotlib is installed, nothing with NBC_COMBINED=0) -- the same files the streaming
+    FolderPipeline writes."""
 
     DEFAULT_MEAN = [0.7399, 0.6139, 0.4401]
     DEFAULT_STD = [0.1068, 0.1272, 0.1271]
@@ -272,10 +274,15 @@ class NeuralBarkCalculator():
                 _, _, fname, wood_type = dataset.samples[i]
                 img = torch.from_numpy(np.ascontiguousarray(fut.result())).to(self.device)
                 mask, counts = self.predict_array(img, excludes_nodes)
-                dual = _DUAL_LUT[mask.cpu().numpy()]          # models.py:349-353: classes 0 / 1 / 2 -> 0 / 127 / 255
-                results_csv.append([fname, wood_type] + self._stats_strings(counts.tolist(), mask.numel()))
+                mask_h = mask.cpu().numpy()
+                dual = _DUAL_LUT[mask_h]                      # models.py:349-353: classes 0 / 1 / 2 -> 0 / 127 / 255
+                stats = self._stats_strings(counts.tolist(), mask.numel())
+                results_csv.append([fname, wood_type] + stats)
                 saves.append(pool.submit(lambda a, d: Image.fromarray(a, mode='L').save(d), dual,
                                          join(output_path, 'outputs', wood_type, fname)))
+                from . import pipeline               # (imports models lazily: no cycle at module load)
+                saves.append(pool.submit(pipeline.write_combined, join(output_path, 'combined_images', wood_type, fname),
+                                         img.cpu().numpy(), mask_h, stats, fname, self.mean, self.std))
             for s in saves:
                 s.result()
         with open(join(output_path, 'final_stats.csv'), 'w') as f:   # as models.py:360-364 (tab-delimited)

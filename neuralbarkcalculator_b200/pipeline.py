@@ -13,6 +13,7 @@ The files are the reference's (same names, same pixels, same CSV); only the PNG 
 import csv
 import os
 import struct
+import threading
 import time
 from concurrent.futures import ThreadPoolExecutor
 from os.path import join
@@ -21,7 +22,7 @@ import numpy as np
 import torch
 from ._png import write_png
 from .dataset import make_dataset
-from . import ops
+from . import figure, ops
 from .engine import PredictEngine
 
 RAW = 4096
@@ -83,6 +84,24 @@ def combined_image(proc, mask, title):
     return canvas
 
 
+_FIGURE_LOCK = threading.Lock()      # pyplot keeps global state: the optional matplotlib renderer runs one figure at a time
+
+
+def write_combined(path, proc, mask, stats, fname, mean, std, png_level=1):
+    """results/combined_images/<wood>/<fname> for one image, by NBC_COMBINED (figure.py): the reference's matplotlib figure
+    ('figure'), the native half-resolution stand-in (default) or nothing ('0').  stats = [bark %, bark mm^2, node %, node
+    mm^2] as the CSV strings (models.py:323-332)."""
+    kind = figure.mode()
+    if kind == 'off':
+        return
+    if kind == 'figure':
+        with _FIGURE_LOCK:
+            figure.save_reference_figure(path, proc, mask, (float(stats[0]), float(stats[2])), mean, std)
+        return
+    title = 'Bark : %.3f;  Node : %.3f   (%s)' % (float(stats[0]), float(stats[2]), fname)     # cf. models.py:334-343
+    write_png(path, combined_image(proc, mask, title), png_level)
+
+
 def bmp_geometry(path):
     """(data offset, bottom_up) of an uncompressed 24-bit RAW x RAW BMP, else None."""
     try:
@@ -109,8 +128,9 @@ class FolderPipeline:
     def __init__(self, calculator, batch=16, io_threads=None, png_compress_level=None):
         if png_compress_level is None:      # 0 = stored (fastest, 1.9 MB per processed image), 1 = fast deflate (default)
             png_compress_level = int(os.environ.get('NBC_PNG_LEVEL', '1'))
-        # results/combined_images/<wood>/<name>.png (the reference always writes its figure); NBC_COMBINED=0 skips it
-        self.combined = os.environ.get('NBC_COMBINED', '1') != '0'
+        # results/combined_images/<wood>/<name>.png (the reference always writes its figure): NBC_COMBINED=0 skips it,
+        # NBC_COMBINED=figure draws the reference's matplotlib figure instead of the native stand-in (figure.py)
+        self.combined = figure.mode() != 'off'
         self.calc = calculator
         self.batch = batch
         self.io_threads = io_threads or max(4, min(32, (os.cpu_count() or 8)))
@@ -181,9 +201,8 @@ class FolderPipeline:
                 write_png(join(out_dual, wood, fname), mask, self.png_level, lut=_DUAL_LUT)
                 rows_csv[i] = [fname, wood] + self.calc._stats_strings(counts, mask.size)
                 if self.combined:
-                    st = rows_csv[i]
-                    title = 'Bark : %.3f;  Node : %.3f   (%s)' % (float(st[2]), float(st[4]), fname)    # cf. models.py:334-343
-                    write_png(join(out_comb, wood, fname), combined_image(proc, mask, title), self.png_level)
+                    write_combined(join(out_comb, wood, fname), proc, mask, rows_csv[i][2:], fname, self.calc.mean, self.calc.std,
+                                   self.png_level)
             timing['save_s'] += time.perf_counter() - t0
 
         readers, writers = ThreadPoolExecutor(self.io_threads), ThreadPoolExecutor(self.io_threads)

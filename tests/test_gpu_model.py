@@ -308,7 +308,7 @@ def test_folder_pipeline_matches_per_image_path(cuda_device, synthetic_sd, tmp_p
     assert pipeline.supported(make_dataset(root))
     rows = pipeline.FolderPipeline(calc, batch=2, io_threads=4).run(root, True)
     assert rows == rows_b
-    for sub in (('processed', 'samples'), ('results', 'outputs')):
+    for sub in (('processed', 'samples'), ('results', 'outputs'), ('results', 'combined_images')):     # both paths: same files
         for wood in synth.WOOD_TYPES:
             d = os.path.join(root, *sub, wood)
             names = sorted(os.listdir(d))
