@@ -41,7 +41,9 @@ __global__ void __launch_bounds__(256) ccl_init(const uint8_t* __restrict__ src,
     int lab = -1;
     if (in) lab = (int)p - __clz(~link << (31 - lane));  // run of set lanes directly below this one
     labels[p] = lab;
-    sizes[p] = 0;
+    // a root is always a pixel that started as its own label (unions only ever lower the label of a root), so only those
+    // counters can be incremented or read later: zeroing them alone saves 4 bytes of writes per pixel
+    if (lab == (int)p) sizes[p] = 0;
   }
 }
 
@@ -133,19 +135,35 @@ __global__ void __launch_bounds__(256) ccl_flatten_count(int H, int W, int thres
   }
 }
 
-// stage A result: setB[p] = background after removing small foreground components
-__global__ void __launch_bounds__(256) ccl_stage_a_apply(const uint8_t* __restrict__ mask, const int* __restrict__ labels,
-                                                         const int* __restrict__ sizes, int threshold,
-                                                         uint8_t* __restrict__ setB, int H, int W,
-                                                         const int* __restrict__ vh) {
+// stage A result + stage B initialisation in one pass: setB[p] = background after removing small foreground components,
+// and at once the run labels of that background set (what ccl_init would compute from setB in another pass over it) in
+// the stage-B label / counter arrays.
+__global__ void __launch_bounds__(256) ccl_stage_a_apply_init_b(const uint8_t* __restrict__ mask, const int* __restrict__ labels,
+                                                                const int* __restrict__ sizes, int threshold,
+                                                                uint8_t* __restrict__ setB, int* __restrict__ labelsB,
+                                                                int* __restrict__ sizesB, int H, int W,
+                                                                const int* __restrict__ vh) {
   const int n = blockIdx.y;
   const int64_t HW = (int64_t)H * W;
   const int64_t live = (int64_t)valid_rows(n, H, vh) * W;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= live) return;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x;
+  if (i0 >= live) return;   // block-uniform
+  const int64_t i = i0 + threadIdx.x;
   const int64_t p = (int64_t)n * HW + i;
-  const bool bg = (mask[p] == 0) || (__ldcg(sizes + labels[p]) < threshold);
-  setB[p] = bg ? 1 : 0;
+  const int lane = threadIdx.x & 31;
+  const bool inb = i < live;
+  const bool in = inb && ((mask[p] == 0) || (__ldcg(sizes + labels[p]) < threshold));
+  const int x = inb ? (int)(i % W) : 0;
+  const unsigned m = __ballot_sync(0xffffffffu, in);
+  const unsigned rowstart = __ballot_sync(0xffffffffu, x == 0);
+  const unsigned link = m & (m << 1) & ~rowstart;
+  if (inb) {
+    setB[p] = in ? 1 : 0;
+    int lab = -1;
+    if (in) lab = (int)p - __clz(~link << (31 - lane));
+    labelsB[p] = lab;
+    if (lab == (int)p) sizesB[p] = 0;
+  }
 }
 
 __global__ void __launch_bounds__(256) ccl_final(uint8_t* __restrict__ mask, const uint8_t* __restrict__ setB,
@@ -186,7 +204,7 @@ using namespace nbc;
 
 extern "C" size_t nbc_ccl_workspace_bytes(int N, int H, int W) {
   const size_t total = (size_t)N * H * W;
-  return align_up(total * 4, 256) * 2 + align_up(total, 256);
+  return align_up(total * 4, 256) * 4 + align_up(total, 256);   // labels + counters of both stages, the stage-B set
 }
 
 static int remove_small_zones_impl(uint8_t* mask, int N, int H, int W, int threshold, int exclude_nodes, int32_t* counts,
@@ -202,7 +220,9 @@ static int remove_small_zones_impl(uint8_t* mask, int N, int H, int W, int thres
   char* ws = reinterpret_cast<char*>(workspace);
   int* labels = reinterpret_cast<int*>(ws);
   int* sizes = reinterpret_cast<int*>(ws + align_up((size_t)total * 4, 256));
-  uint8_t* setB = reinterpret_cast<uint8_t*>(ws + 2 * align_up((size_t)total * 4, 256));
+  int* labelsB = reinterpret_cast<int*>(ws + 2 * align_up((size_t)total * 4, 256));
+  int* sizesB = reinterpret_cast<int*>(ws + 3 * align_up((size_t)total * 4, 256));
+  uint8_t* setB = reinterpret_cast<uint8_t*>(ws + 4 * align_up((size_t)total * 4, 256));
   const int64_t HW = (int64_t)H * W;
   const dim3 grid((unsigned)ceil_div64(HW, 256), N);
   NBC_CUDA(cudaMemsetAsync(counts, 0, (size_t)N * 3 * sizeof(int32_t), stream));
@@ -213,16 +233,15 @@ static int remove_small_zones_impl(uint8_t* mask, int N, int H, int W, int thres
   NBC_CHECK_LAUNCH();
   ccl_flatten_count<<<grid, 256, 0, stream>>>(H, W, threshold, labels, sizes, vh);
   NBC_CHECK_LAUNCH();
-  ccl_stage_a_apply<<<grid, 256, 0, stream>>>(mask, labels, sizes, threshold, setB, H, W, vh);
+  // stage B: background components of the stage-A result (its own label / counter arrays: the fused kernel still reads
+  // stage A's while it writes them)
+  ccl_stage_a_apply_init_b<<<grid, 256, 0, stream>>>(mask, labels, sizes, threshold, setB, labelsB, sizesB, H, W, vh);
   NBC_CHECK_LAUNCH();
-  // stage B: background components of the stage-A result
-  ccl_init<<<grid, 256, 0, stream>>>(setB, H, W, labels, sizes, vh);
+  ccl_merge<<<grid, 256, 0, stream>>>(setB, H, W, labelsB, vh);
   NBC_CHECK_LAUNCH();
-  ccl_merge<<<grid, 256, 0, stream>>>(setB, H, W, labels, vh);
+  ccl_flatten_count<<<grid, 256, 0, stream>>>(H, W, threshold, labelsB, sizesB, vh);
   NBC_CHECK_LAUNCH();
-  ccl_flatten_count<<<grid, 256, 0, stream>>>(H, W, threshold, labels, sizes, vh);
-  NBC_CHECK_LAUNCH();
-  ccl_final<<<grid, 256, 0, stream>>>(mask, setB, labels, sizes, threshold, exclude_nodes, H, W, counts, vh);
+  ccl_final<<<grid, 256, 0, stream>>>(mask, setB, labelsB, sizesB, threshold, exclude_nodes, H, W, counts, vh);
   NBC_CHECK_LAUNCH();
   return 0;
 }

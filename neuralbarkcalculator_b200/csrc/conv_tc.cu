@@ -50,6 +50,7 @@ struct ConvTcParams {
   // beyond it are written as zeros (at least kRaggedHalo of them: the zero padding the next layer reads); tiles
   // that start beyond the halo are skipped.
   const int* valid_h;
+  int ragged_compact;   // 1: walk the compact enumeration of live M tiles (ragged_map_setup); 0: dense numbering, dead tiles skipped
   int8_t tap_map[9];
   int16_t tap_dh[9];
   int16_t tap_dw[9];
@@ -120,7 +121,7 @@ __device__ __forceinline__ bool tile_dead(const ConvTcParams& p, int tile) {
 // index maps back to the dense m_tile the rest of the kernel works with.
 static_assert((kMaxRaggedImages + 1) * 4 <= kMapBytes, "ragged map");
 __device__ __forceinline__ bool ragged_map_setup(const ConvTcParams& p, int* s_map) {
-  const bool mapped = p.valid_h != nullptr && p.N <= kMaxRaggedImages;   // uniform over the grid
+  const bool mapped = p.valid_h != nullptr && p.ragged_compact != 0 && p.N <= kMaxRaggedImages;   // uniform over the grid
   if (mapped) {
     if (threadIdx.x == 0) {
       int acc = 0;
@@ -135,17 +136,32 @@ __device__ __forceinline__ bool ragged_map_setup(const ConvTcParams& p, int* s_m
   }
   return mapped;
 }
-// dense m_tile of virtual M index vm (num_m_tiles = "beyond the last": a phantom for the pair kernel)
-__device__ __forceinline__ int ragged_real_m(const ConvTcParams& p, const int* s_map, int vm) {
+// dense m_tile of virtual M index vm (num_m_tiles = "beyond the last": a phantom for the pair kernel).  `hint` is the
+// caller's cursor (the image of its previous lookup): every walker visits its tiles in increasing order, so the search
+// is one or two shared-memory reads, not a scan -- this runs once per tile in single threads that pace the pipeline.
+__device__ __forceinline__ int ragged_real_m(const ConvTcParams& p, const int* s_map, int vm, int& hint) {
   if (s_map == nullptr) return vm;
   if (vm >= s_map[p.N]) return p.num_m_tiles;
-  int img = 0;
+  int img = (s_map[hint] <= vm) ? hint : 0;
   while (s_map[img + 1] <= vm) ++img;
+  hint = img;
   return img * p.tiles_h * p.tiles_w + (vm - s_map[img]);
 }
-__device__ __forceinline__ int ragged_real_tile(const ConvTcParams& p, const int* s_map, int vt) {
-  if (s_map == nullptr) return vt;
-  return ragged_real_m(p, s_map, vt / p.num_n_tiles) * p.num_n_tiles + vt % p.num_n_tiles;
+// a virtual tile of the walk: coordinates + "dead" (starts at or below the last valid row of its image: no loads, no MMA)
+struct VTile {
+  TileCoord t;
+  bool dead;
+};
+__device__ __forceinline__ VTile vtile(const ConvTcParams& p, const int* s_map, int vt, int& hint) {
+  int tile = vt;
+  if (s_map != nullptr) {
+    const int vm = vt / p.num_n_tiles;
+    tile = ragged_real_m(p, s_map, vm, hint) * p.num_n_tiles + (vt - vm * p.num_n_tiles);
+  }
+  VTile v;
+  v.t = tile_coord(p, tile);
+  v.dead = p.valid_h != nullptr && v.t.h0 >= __ldg(p.valid_h + v.t.img);
+  return v;
 }
 // output group handled by local step j of a tile (see the epilogue): half 0 of the epilogue warps owns the even
 // steps, half 1 the odd ones; each half walks its own contiguous range of channels
@@ -217,10 +233,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     // ================================ TMA producer ================================
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
+      int hint = 0;
       for (int vt = blockIdx.x; vt < total_tiles; vt += gridDim.x) {
-        const int tile = ragged_real_tile(p, s_map, vt);
-        if (tile_dead(p, tile)) continue;
-        const TileCoord t = tile_coord(p, tile);
+        const VTile v = vtile(p, s_map, vt, hint);
+        if (v.dead) continue;
+        const TileCoord t = v.t;
         const int n0 = t.n_tile * BN;
         for (int tap = 0; tap < p.n_taps; ++tap) {
           const CUtensorMap* mA = &p.tmA[p.tap_map[tap]];
@@ -256,9 +273,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     if (elect_one()) {
       constexpr uint32_t idesc = F16 ? umma_idesc_f16(128, BN) : umma_idesc_bf16(128, BN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      int hint = 0;
       for (int vt = blockIdx.x; vt < total_tiles; vt += gridDim.x) {
-        const int tile = ragged_real_tile(p, s_map, vt);
-        if (tile_dead(p, tile)) continue;
+        if (vtile(p, s_map, vt, hint).dead) continue;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 300 + (int)acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -291,21 +308,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     // PLACE and the same buffer then leaves through a TMA store (full 128-byte lines, no partial-sector writes).
     if (elect_one()) {
       constexpr int kAhead = RES ? OB - 1 : 0;
-      int ld_tile = blockIdx.x;
-      while (ld_tile < total_tiles && tile_dead(p, ragged_real_tile(p, s_map, ld_tile))) ld_tile += gridDim.x;
-      int st_tile = ld_tile, ld_j = 0, st_j = 0;
+      // two cursors over this CTA's live tiles: ld (residual prefetch, runs ahead) and st (output stores)
+      int ld_tile = blockIdx.x, st_tile = blockIdx.x, ld_hint = 0, st_hint = 0, ld_j = 0, st_j = 0;
+      TileCoord ld_t{}, st_t{};
+      auto ld_seek = [&]() {
+        for (; ld_tile < total_tiles; ld_tile += gridDim.x) {
+          const VTile v = vtile(p, s_map, ld_tile, ld_hint);
+          ld_t = v.t;
+          if (!v.dead) break;
+        }
+      };
+      auto st_seek = [&]() {
+        for (; st_tile < total_tiles; st_tile += gridDim.x) {
+          const VTile v = vtile(p, s_map, st_tile, st_hint);
+          st_t = v.t;
+          if (!v.dead) break;
+        }
+      };
+      ld_seek();
+      st_seek();
       uint32_t ld_s = 0, st_s = 0;
       auto issue_load = [&]() {
-        const TileCoord t = tile_coord(p, ragged_real_tile(p, s_map, ld_tile));
         const uint32_t b = ld_s % OB;
         mbar_expect_tx(&bufready_bar[b], kOutBufBytes);
-        tma_load_4d(obuf + b * kOutBufBytes, &p.tmRes, &bufready_bar[b], t.n_tile * BN + step_group<kSteps>(ld_j) * 64, t.w0,
-                    t.h0, t.img);
+        tma_load_4d(obuf + b * kOutBufBytes, &p.tmRes, &bufready_bar[b], ld_t.n_tile * BN + step_group<kSteps>(ld_j) * 64, ld_t.w0,
+                    ld_t.h0, ld_t.img);
         ++ld_s;
         if (++ld_j == kSteps) {
           ld_j = 0;
           ld_tile += gridDim.x;
-          while (ld_tile < total_tiles && tile_dead(p, ragged_real_tile(p, s_map, ld_tile))) ld_tile += gridDim.x;
+          ld_seek();
         }
       };
       if (RES) {
@@ -318,8 +350,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         }
         const uint32_t b = st_s % OB;
         mbar_wait(&outready_bar[b], (st_s / OB) & 1u, 500 + (int)b);
-        const TileCoord t = tile_coord(p, ragged_real_tile(p, s_map, st_tile));
-        tma_store_4d(&p.tmOut, obuf + b * kOutBufBytes, t.n_tile * BN + step_group<kSteps>(st_j) * 64, t.w0, t.h0, t.img);
+        tma_store_4d(&p.tmOut, obuf + b * kOutBufBytes, st_t.n_tile * BN + step_group<kSteps>(st_j) * 64, st_t.w0, st_t.h0, st_t.img);
         tma_store_commit();
         if (!RES) {
           tma_store_wait_read<0>();
@@ -329,7 +360,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         if (++st_j == kSteps) {
           st_j = 0;
           st_tile += gridDim.x;
-          while (st_tile < total_tiles && tile_dead(p, ragged_real_tile(p, s_map, st_tile))) st_tile += gridDim.x;
+          st_seek();
         }
       }
       tma_store_wait_all();
@@ -351,9 +382,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     const uint32_t rsw = (uint32_t)(row & 7);
     const int u0 = (BN == 64) ? half * 4 : 0;
     uint32_t acc = 0, acc_phase = 0, live_tiles = 0;
+    int hint = 0;
     for (int vt = blockIdx.x; vt < total_tiles; vt += gridDim.x) {
-        const int tile = ragged_real_tile(p, s_map, vt);
-      const TileCoord t = tile_coord(p, tile);
+      const TileCoord t = vtile(p, s_map, vt, hint).t;
       const int vh = p.valid_h != nullptr ? __ldg(p.valid_h + t.img) : INT_MAX;
       const int h = t.h0 + (row >> p.tw_log2), w = t.w0 + (row & (p.tw - 1));
       if (t.h0 >= vh) {
@@ -461,14 +492,20 @@ __device__ __forceinline__ bool mtile_dead(const ConvTcParams& p, int m_tile) {
   const int mt = m_tile / p.tiles_w;
   return (mt % p.tiles_h) * p.th >= __ldg(p.valid_h + mt / p.tiles_h);
 }
-// pair tiles are numbered over (virtual, see ragged_map_setup) M pairs; the two M tiles of a pair need not be neighbours
-__device__ __forceinline__ bool pair_dead(const ConvTcParams& p, const int* s_map, int pair_tile) {
-  const int mp = pair_tile / p.num_n_tiles;
-  return mtile_dead(p, ragged_real_m(p, s_map, 2 * mp)) && mtile_dead(p, ragged_real_m(p, s_map, 2 * mp + 1));
-}
-// this CTA's tile (dense single-CTA numbering) of a pair tile
-__device__ __forceinline__ int pair_my_tile(const ConvTcParams& p, const int* s_map, int pair_tile, int rank) {
-  return ragged_real_m(p, s_map, 2 * (pair_tile / p.num_n_tiles) + rank) * p.num_n_tiles + pair_tile % p.num_n_tiles;
+// pair tiles are numbered over (virtual, see ragged_map_setup) M pairs; the two M tiles of a pair need not be neighbours.
+// PairTile = this CTA's own tile of pair tile pt (dense single-CTA coordinates) + "both tiles of the pair are dead".
+struct PairTile {
+  TileCoord t;
+  bool dead;
+};
+__device__ __forceinline__ PairTile pair_tile(const ConvTcParams& p, const int* s_map, int pt, int rank, int& hint) {
+  const int mp = pt / p.num_n_tiles, n = pt - mp * p.num_n_tiles;
+  const int m0 = ragged_real_m(p, s_map, 2 * mp, hint);
+  const int m1 = ragged_real_m(p, s_map, 2 * mp + 1, hint);
+  PairTile r;
+  r.dead = mtile_dead(p, m0) && mtile_dead(p, m1);
+  r.t = tile_coord(p, (rank ? m1 : m0) * p.num_n_tiles + n);
+  return r;
 }
 
 template <int BN, int OB, bool RES, bool RELU, bool F16>
@@ -537,9 +574,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
       const uint32_t full0 = mapa_shared(smem_u32(&full_bar[0]), 0);   // the leader's full barriers
+      int hint = 0;
       for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
-        if (pair_dead(p, s_map, pt)) continue;
-        const TileCoord t = tile_coord(p, pair_my_tile(p, s_map, pt, rank));
+        const PairTile pr = pair_tile(p, s_map, pt, rank, hint);
+        if (pr.dead) continue;
+        const TileCoord t = pr.t;
         const int n0 = t.n_tile * BN + rank * (BN / 2);
         for (int kb = 0; kb < kblocks; ++kb) {
           const CUtensorMap* mA;
@@ -574,8 +613,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     if (leader && elect_one()) {
       constexpr uint32_t idesc = F16 ? umma_idesc_f16(256, BN) : umma_idesc_bf16(256, BN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      int hint = 0;
       for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
-        if (pair_dead(p, s_map, pt)) continue;
+        if (pair_tile(p, s_map, pt, rank, hint).dead) continue;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 300 + (int)acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -605,21 +645,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     // ================================ output / residual TMA (per CTA, own tile) ================================
     if (elect_one()) {
       constexpr int kAhead = RES ? OB - 1 : 0;
-      int ld_pt = cluster_id;
-      while (ld_pt < total_pairs && pair_dead(p, s_map, ld_pt)) ld_pt += num_clusters;
-      int st_pt = ld_pt, ld_j = 0, st_j = 0;
+      int ld_pt = cluster_id, st_pt = cluster_id, ld_hint = 0, st_hint = 0, ld_j = 0, st_j = 0;
+      TileCoord ld_t{}, st_t{};
+      auto ld_seek = [&]() {
+        for (; ld_pt < total_pairs; ld_pt += num_clusters) {
+          const PairTile pr = pair_tile(p, s_map, ld_pt, rank, ld_hint);
+          ld_t = pr.t;
+          if (!pr.dead) break;
+        }
+      };
+      auto st_seek = [&]() {
+        for (; st_pt < total_pairs; st_pt += num_clusters) {
+          const PairTile pr = pair_tile(p, s_map, st_pt, rank, st_hint);
+          st_t = pr.t;
+          if (!pr.dead) break;
+        }
+      };
+      ld_seek();
+      st_seek();
       uint32_t ld_s = 0, st_s = 0;
       auto issue_load = [&]() {
-        const TileCoord t = tile_coord(p, pair_my_tile(p, s_map, ld_pt, rank));
         const uint32_t b = ld_s % OB;
         mbar_expect_tx(&bufready_bar[b], kOutBufBytes);
-        tma_load_4d(obuf + b * kOutBufBytes, &p.tmRes, &bufready_bar[b], t.n_tile * BN + step_group<kSteps>(ld_j) * 64, t.w0,
-                    t.h0, t.img);
+        tma_load_4d(obuf + b * kOutBufBytes, &p.tmRes, &bufready_bar[b], ld_t.n_tile * BN + step_group<kSteps>(ld_j) * 64, ld_t.w0,
+                    ld_t.h0, ld_t.img);
         ++ld_s;
         if (++ld_j == kSteps) {
           ld_j = 0;
           ld_pt += num_clusters;
-          while (ld_pt < total_pairs && pair_dead(p, s_map, ld_pt)) ld_pt += num_clusters;
+          ld_seek();
         }
       };
       if (RES) {
@@ -632,8 +686,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         }
         const uint32_t b = st_s % OB;
         mbar_wait(&outready_bar[b], (st_s / OB) & 1u, 500 + (int)b);
-        const TileCoord t = tile_coord(p, pair_my_tile(p, s_map, st_pt, rank));
-        tma_store_4d(&p.tmOut, obuf + b * kOutBufBytes, t.n_tile * BN + step_group<kSteps>(st_j) * 64, t.w0, t.h0, t.img);
+        tma_store_4d(&p.tmOut, obuf + b * kOutBufBytes, st_t.n_tile * BN + step_group<kSteps>(st_j) * 64, st_t.w0, st_t.h0, st_t.img);
         tma_store_commit();
         if (!RES) {
           tma_store_wait_read<0>();
@@ -643,7 +696,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         if (++st_j == kSteps) {
           st_j = 0;
           st_pt += num_clusters;
-          while (st_pt < total_pairs && pair_dead(p, s_map, st_pt)) st_pt += num_clusters;
+          st_seek();
         }
       }
       tma_store_wait_all();
@@ -661,13 +714,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     const uint32_t rsw = (uint32_t)(row & 7);
     const uint32_t tempty0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);   // the leader's accumulator-empty barriers
     uint32_t acc = 0, acc_phase = 0, live_tiles = 0;
+    int hint = 0;
     for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
-      const int tile = pair_my_tile(p, s_map, pt, rank);
-      const TileCoord t = tile_coord(p, tile);
+      const PairTile pr = pair_tile(p, s_map, pt, rank, hint);
+      const TileCoord t = pr.t;
       const bool phantom = t.img >= p.N;
       const int vh = phantom ? 0 : (p.valid_h != nullptr ? __ldg(p.valid_h + t.img) : INT_MAX);
       const int h = t.h0 + (row >> p.tw_log2), w = t.w0 + (row & (p.tw - 1));
-      if (pair_dead(p, s_map, pt)) {
+      if (pr.dead) {
         if (!phantom && t.h0 < vh + kRaggedHalo && w < p.Wo && h < p.Ho && h < vh + kRaggedHalo) {
           constexpr int kColsZ = BN / 2;
           __nv_bfloat16* o = p.out + (((int64_t)t.img * p.Ho + h) * p.Wo + w) * p.Cout + t.n_tile * BN + half * kColsZ;
@@ -829,10 +883,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_stem_kernel(const __gri
       for (int ky = 0; ky < 7; ++ky) tma_load_2d(wres + ky * 4096, &p.tmB, w_bar, ky * 32, 0);
       uint32_t stage = 0, phase = 0;
       const int64_t row_bytes = (int64_t)p.stem_wp * 8;
+      int hint = 0;
       for (int vt = blockIdx.x; vt < total_tiles; vt += gridDim.x) {
-        const int tile = ragged_real_tile(p, s_map, vt);
-        if (tile_dead(p, tile)) continue;
-        const TileCoord t = tile_coord(p, tile);      // tw = 128, th = 1: h0 = output row, w0 = first output column
+        const VTile v = vtile(p, s_map, vt, hint);
+        if (v.dead) continue;
+        const TileCoord t = v.t;      // tw = 128, th = 1: h0 = output row, w0 = first output column
         // what is left of the padded row from pixel 2 * w0 on (a multiple of 16 bytes); beyond it lie outputs >= Wo
         const uint32_t len = (uint32_t)min((int64_t)(2 * 127 + 8) * 8, row_bytes - (int64_t)t.w0 * 16);
         mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + (int)stage);
@@ -854,9 +909,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_stem_kernel(const __gri
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       mbar_wait(w_bar, 0, 700);
       const uint32_t w_addr = smem_u32(wres);
+      int hint = 0;
       for (int vt = blockIdx.x; vt < total_tiles; vt += gridDim.x) {
-        const int tile = ragged_real_tile(p, s_map, vt);
-        if (tile_dead(p, tile)) continue;
+        if (vtile(p, s_map, vt, hint).dead) continue;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 300 + (int)acc);
         mbar_wait(&full_bar[stage], phase, 200 + (int)stage);
         tc_fence_after();
@@ -885,12 +940,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_stem_kernel(const __gri
     // ================================ output TMA ================================
     if (elect_one()) {
       uint32_t st_s = 0;
+      int hint = 0;
       for (int vt = blockIdx.x; vt < total_tiles; vt += gridDim.x) {
-        const int tile = ragged_real_tile(p, s_map, vt);
-        if (tile_dead(p, tile)) continue;
+        const VTile v = vtile(p, s_map, vt, hint);
+        if (v.dead) continue;
         const uint32_t b = st_s % OB;
         mbar_wait(&outready_bar[b], (st_s / OB) & 1u, 500 + (int)b);
-        const TileCoord t = tile_coord(p, tile);
+        const TileCoord t = v.t;
         tma_store_4d(&p.tmOut, obuf + b * kOutBufBytes, 0, t.w0, t.h0, t.img);
         tma_store_commit();
         tma_store_wait_read<0>();
@@ -910,9 +966,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_stem_kernel(const __gri
     const uint32_t rsw = (uint32_t)(row & 7);
     const int u0 = half * 4;
     uint32_t acc = 0, acc_phase = 0, live_tiles = 0;
+    int hint = 0;
     for (int vt = blockIdx.x; vt < total_tiles; vt += gridDim.x) {
-        const int tile = ragged_real_tile(p, s_map, vt);
-      const TileCoord t = tile_coord(p, tile);
+      const TileCoord t = vtile(p, s_map, vt, hint).t;
       const int vh = p.valid_h != nullptr ? __ldg(p.valid_h + t.img) : INT_MAX;
       const int h = t.h0, w = t.w0 + row;
       if (t.h0 >= vh) {
@@ -967,6 +1023,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_stem_kernel(const __gri
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
+// NBC_RAGGED_COMPACT=0 switches the compact tile enumeration of ragged batches off (A/B measurements)
+static int ragged_compact_default() {
+  static const int v = [] {
+    const char* e = getenv("NBC_RAGGED_COMPACT");
+    return (e && *e) ? atoi(e) : 1;
+  }();
+  return v;
+}
+
 static int encode_act_map(CUtensorMap* m, const void* base, uint64_t C, uint64_t Wd, uint64_t Hd, uint64_t Nd,
                           uint64_t strideW, uint64_t strideH, uint64_t strideN, uint32_t boxW, uint32_t boxH,
                           uint32_t boxC = 64) {
@@ -1311,6 +1376,7 @@ int conv_tc_prepare_stem(int N, int Ho, int Wo, int Hp, int Wp, const void* padd
   p.n_taps = 7, p.cblocks = 1, p.relu = relu;
   p.bias = bias, p.residual = nullptr, p.out = reinterpret_cast<__nv_bfloat16*>(y);
   p.valid_h = valid_h;
+  p.ragged_compact = ragged_compact_default();
   L->block_n = 64, L->kblk = 32;
   const char* base = reinterpret_cast<const char*>(padded);
   const uint64_t row_bytes = (uint64_t)Wp * 8;
@@ -1353,6 +1419,7 @@ int conv_tc_prepare(const ConvGeom& g, const void* x, const void* w, const float
   ConvTcLaunch* L = reinterpret_cast<ConvTcLaunch*>(out->storage);
   int rc = build_launch(g, x, w, bias, residual, y, L);
   L->p.valid_h = valid_h;
+  L->p.ragged_compact = ragged_compact_default();
   return rc;
 }
 
@@ -1376,6 +1443,7 @@ int conv_tc_prepare_dual(const ConvGeom& g, const void* x, const ConvGeom& g2, c
   if (rc) return rc;
   ConvTcParams& p = L->p;
   p.valid_h = valid_h;
+  p.ragged_compact = ragged_compact_default();
   const uint64_t eb = 2;
   const char* xb = reinterpret_cast<const char*>(x2);
   p.map2 = 1;        // the main source is a stride-1 convolution: it only uses tmA[0]
