@@ -62,6 +62,13 @@ int nbc_preprocess_4x_span_u8(const uint8_t* raw_span, int H, int W, int64_t pit
                               uint8_t* out, int32_t* first_last, void* workspace, size_t workspace_bytes, void* stream);
 int nbc_host_zero_row_span(const uint8_t* raw, int H, int64_t pitch, int64_t row_bytes, int group, int32_t* row0,
                            int32_t* rows);
+/* A CHUNK of n scans in three launches (what the engine issues per ragged batch; the per-scan calls above are n = 1):
+ * raw_spans / span_row0 / span_rows are HOST arrays of n entries (device pointers and spans as above; the span arrays may
+ * be NULL = whole scans), result i goes to out + i * out_stride_bytes, its {first,last} to first_last + 2 i.
+ * workspace >= n * nbc_preprocess_workspace_bytes(H, W). */
+int nbc_preprocess_4x_batch_u8(const uint8_t* const* raw_spans, const int32_t* span_row0, const int32_t* span_rows, int n, int H,
+                               int W, int64_t pitch, int flags, uint8_t* out, int64_t out_stride_bytes, int32_t* first_last,
+                               void* workspace, size_t workspace_bytes, void* stream);
 /* General ratio: any H x W image whose larger side exceeds `target` becomes target x target (models.py:194-198,
  * skimage resize order 3, mode 'reflect', no anti-aliasing, clipped to the input range), then trim_black and the
  * float -> u8 rounding -- float64 arithmetic in the order of oracle/preprocess.py::resize_general_f64.  Same flags,

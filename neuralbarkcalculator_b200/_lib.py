@@ -23,6 +23,8 @@ SIGNATURES = {
     'nbc_preprocess_4x_u8': (c_int, [c_void_p, c_int, c_int, c_i64, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'nbc_preprocess_4x_span_u8': (c_int, [c_void_p, c_int, c_int, c_i64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                                           c_void_p]),
+    'nbc_preprocess_4x_batch_u8': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_i64, c_int, c_void_p, c_i64, c_void_p,
+                                           c_void_p, c_size_t, c_void_p]),
     'nbc_host_zero_row_span': (c_int, [c_void_p, c_int, c_i64, c_i64, c_int, c_void_p, c_void_p]),
     'nbc_preprocess_general_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'nbc_preprocess_general_u8': (c_int, [c_void_p, c_int, c_int, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,

@@ -23,6 +23,16 @@ struct PreHeader {
   int pad[2];
 };
 
+// One launch handles up to kPreBatch scans (blockIdx.z = scan): a chunk of the engine's ragged batch goes through K1 in
+// three launches instead of three per scan (the small trim / clamp kernels are launch-latency bound: 5 us each for
+// microseconds of work).  Scan z reads raw[z] (memory rows [lo[z], hi[z]) are really there, the rest are zero by
+// definition), uses the workspace slice z (header, row counts, the saturated u8 intermediate) and writes result z.
+constexpr int kPreBatch = 16;
+struct PreBatch {
+  const uint8_t* raw[kPreBatch];
+  int lo[kPreBatch], hi[kPreBatch];
+};
+
 __device__ __forceinline__ int byte_of(uint32_t v, int i) { return (v >> (8 * i)) & 0xFF; }
 
 // The 48 source bytes of 4 output pixels on each of the 4 source rows of output row ho (zero where the thread is idle)
@@ -67,10 +77,16 @@ __device__ __forceinline__ void pass1_load(const uint8_t* __restrict__ raw, int 
 // is all zero BY DEFINITION (the host found the scan's dark bands, nbc_host_zero_row_span, and copied only the rows in
 // between) -- such a group of four rows is never dereferenced and contributes min = max = 0, S = 0.
 template <bool kAligned>
-__global__ void __launch_bounds__(256) resize4x_pass1(const uint8_t* __restrict__ raw, int H, int W, int64_t pitch,
-                                                      int flags, uint8_t* __restrict__ r8, PreHeader* hdr,
-                                                      int* __restrict__ rowcount, int span_lo, int span_hi) {
+__global__ void __launch_bounds__(256) resize4x_pass1(const __grid_constant__ PreBatch batch, int H, int W, int64_t pitch,
+                                                      int flags, uint8_t* __restrict__ hdrs, size_t hdr_stride,
+                                                      uint8_t* __restrict__ r8s, size_t r8_stride) {
   __shared__ __align__(16) uint32_t s_out[8][96];   // per warp: 32 threads x 12 bytes
+  const int z = blockIdx.z;
+  const uint8_t* __restrict__ raw = batch.raw[z];
+  const int span_lo = batch.lo[z], span_hi = batch.hi[z];
+  PreHeader* hdr = reinterpret_cast<PreHeader*>(hdrs + z * hdr_stride);
+  int* __restrict__ rowcount = reinterpret_cast<int*>(hdrs + z * hdr_stride + sizeof(PreHeader));
+  uint8_t* __restrict__ r8 = r8s + z * r8_stride;
   const int Wo = W >> 2;
   const int groups = (Wo + 3) >> 2;  // 4 output pixels per thread
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -185,9 +201,14 @@ __global__ void __launch_bounds__(256) rowcount_u8(const uint8_t* __restrict__ i
 
 // trim_black row rule (models.py:160-164): keep[r] = count/W > 0.85; first = argmax(keep);
 // last = H - argmax(keep[::-1]); nothing kept -> (0, H).  all_nondark: min(in) >= 1 makes every pixel non-dark.
+// One block per scan: block z reads the row counts / header `ws_stride` bytes after those of block z - 1 (0 for a single
+// scan) and writes first_last + 2 z.
 __global__ void __launch_bounds__(1024) trim_rows_kernel(const int* __restrict__ rowcount, const PreHeader* hdr,
-                                                         int Ho, int Wo, int square, int32_t* first_last) {
+                                                         int Ho, int Wo, int square, int32_t* first_last, size_t ws_stride = 0) {
   __shared__ int s_first, s_last_from_end;
+  rowcount = reinterpret_cast<const int*>(reinterpret_cast<const char*>(rowcount) + blockIdx.x * ws_stride);
+  if (hdr) hdr = reinterpret_cast<const PreHeader*>(reinterpret_cast<const char*>(hdr) + blockIdx.x * ws_stride);
+  first_last += 2 * blockIdx.x;
   if (threadIdx.x == 0) s_first = INT_MAX, s_last_from_end = INT_MAX;
   __syncthreads();
   const bool all_nondark = hdr && (255 - hdr->inv_min) >= 1;
@@ -211,9 +232,15 @@ __global__ void __launch_bounds__(1024) trim_rows_kernel(const int* __restrict__
   }
 }
 
-__global__ void __launch_bounds__(256) resize4x_pass2(const uint8_t* __restrict__ r8, const PreHeader* hdr, int Wo,
-                                                      const int32_t* __restrict__ first_last,
-                                                      uint8_t* __restrict__ out) {
+__global__ void __launch_bounds__(256) resize4x_pass2(const uint8_t* __restrict__ hdrs, size_t hdr_stride,
+                                                      const uint8_t* __restrict__ r8s, size_t r8_stride, int Wo,
+                                                      const int32_t* __restrict__ first_last_all,
+                                                      uint8_t* __restrict__ out_all, int64_t out_stride) {
+  const int z = blockIdx.y;
+  const uint8_t* __restrict__ r8 = r8s + z * r8_stride;
+  const PreHeader* hdr = reinterpret_cast<const PreHeader*>(hdrs + z * hdr_stride);
+  const int32_t* first_last = first_last_all + 2 * z;
+  uint8_t* __restrict__ out = out_all + z * out_stride;
   const int first = first_last[0], last = first_last[1];
   const uint32_t lo = (uint32_t)(255 - hdr->inv_min), hi = (uint32_t)hdr->max;
   const uint32_t lo4 = lo * 0x01010101u, hi4 = hi * 0x01010101u;
@@ -347,48 +374,83 @@ extern "C" size_t nbc_preprocess_workspace_bytes(int H, int W) {
   return pre_header_bytes(Ho > H ? Ho : H) + align_up((size_t)Ho * Wo * 3 * sizeof(int16_t), 256);
 }
 
+static int preprocess_4x_batch(const uint8_t* const* raw_spans, const int32_t* span_row0, const int32_t* span_rows, int n, int H,
+                               int W, int64_t pitch, int flags, uint8_t* out, int64_t out_stride, int32_t* first_last,
+                               void* workspace, size_t workspace_bytes, cudaStream_t stream, const char* who) {
+  NBC_REQUIRE(raw_spans && out && first_last && workspace && n > 0, "%s: null pointer", who);
+  NBC_REQUIRE(H > 0 && W > 0 && H % 4 == 0 && W % 4 == 0, "%s: H and W must be multiples of 4 (got %dx%d)", who, H, W);
+  NBC_REQUIRE(pitch >= (int64_t)W * 3, "%s: pitch %lld < 3*W", who, (long long)pitch);
+  const size_t ws_stride = nbc_preprocess_workspace_bytes(H, W);
+  if (workspace_bytes < ws_stride * (size_t)n) {
+    set_error("%s: workspace %zu < %zu", who, workspace_bytes, ws_stride * (size_t)n);
+    return NBC_ERR_WORKSPACE;
+  }
+  const int Ho = H / 4, Wo = W / 4;
+  // workspace: n headers (min / max + per-row non-dark counts) first -- one memset clears them all -- then the n saturated
+  // u8 intermediates (Ho x Wo x 3 each)
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  const size_t hdr_stride = pre_header_bytes(H), r8_stride = ws_stride - hdr_stride;
+  uint8_t* r8s = ws + (size_t)n * hdr_stride;
+  NBC_CUDA(cudaMemsetAsync(ws, 0, (size_t)n * hdr_stride, stream));
+  bool aligned = pitch % 16 == 0;
+  for (int i = 0; i < n; ++i) {
+    const int r0 = span_row0 ? span_row0[i] : 0, rows = span_rows ? span_rows[i] : H;
+    NBC_REQUIRE((raw_spans[i] || rows == 0) && r0 >= 0 && rows >= 0 && r0 % 4 == 0 && rows % 4 == 0 && r0 + rows <= H,
+                "%s: the span [%d, +%d) of scan %d must be made of whole groups of 4 rows inside the image", who, r0, rows, i);
+    aligned = aligned && (reinterpret_cast<uintptr_t>(raw_spans[i]) % 16 == 0);
+  }
+  const int groups = (Wo + 3) / 4;
+  const int64_t total16 = ceil_div64((int64_t)Ho * Wo * 3, 16);
+  const int blocks2 = (int)(total16 < 256 ? 1 : (ceil_div64(total16, 256) < 4 * 148 ? ceil_div64(total16, 256) : 4 * 148));
+  for (int i0 = 0; i0 < n; i0 += kPreBatch) {
+    const int nb = n - i0 < kPreBatch ? n - i0 : kPreBatch;
+    PreBatch b;
+    for (int j = 0; j < kPreBatch; ++j) {
+      const int i = i0 + (j < nb ? j : 0);
+      const int r0 = span_row0 ? span_row0[i] : 0, rows = span_rows ? span_rows[i] : H;
+      // the kernel addresses memory row r at raw + r * pitch and never touches a row outside the span
+      b.raw[j] = raw_spans[i] ? raw_spans[i] - (int64_t)r0 * pitch : ws;
+      b.lo[j] = r0, b.hi[j] = r0 + rows;
+    }
+    const dim3 grid(ceil_div(groups, 256), Ho, nb);
+    if (aligned)
+      resize4x_pass1<true><<<grid, 256, 0, stream>>>(b, H, W, pitch, flags, ws + i0 * hdr_stride, hdr_stride, r8s + i0 * r8_stride,
+                                                     r8_stride);
+    else
+      resize4x_pass1<false><<<grid, 256, 0, stream>>>(b, H, W, pitch, flags, ws + i0 * hdr_stride, hdr_stride, r8s + i0 * r8_stride,
+                                                      r8_stride);
+    NBC_CHECK_LAUNCH();
+  }
+  trim_rows_kernel<<<n, 1024, 0, stream>>>(reinterpret_cast<const int*>(ws + sizeof(PreHeader)), reinterpret_cast<const PreHeader*>(ws),
+                                          Ho, Wo, Ho == Wo ? 1 : 0, first_last, hdr_stride);
+  NBC_CHECK_LAUNCH();
+  resize4x_pass2<<<dim3(blocks2, n), 256, 0, stream>>>(ws, hdr_stride, r8s, r8_stride, Wo, first_last, out, out_stride);
+  NBC_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int nbc_preprocess_4x_u8(const uint8_t* raw, int H, int W, int64_t pitch, int flags, uint8_t* out,
                                     int32_t* first_last, void* workspace, size_t workspace_bytes, void* stream_) {
-  return nbc_preprocess_4x_span_u8(raw, H, W, pitch, flags, 0, H, out, first_last, workspace, workspace_bytes, stream_);
+  NBC_REQUIRE(raw, "nbc_preprocess_4x_u8: null pointer");
+  return preprocess_4x_batch(&raw, nullptr, nullptr, 1, H, W, pitch, flags, out, 0, first_last, workspace, workspace_bytes,
+                             reinterpret_cast<cudaStream_t>(stream_), "nbc_preprocess_4x_u8");
 }
 
 extern "C" int nbc_preprocess_4x_span_u8(const uint8_t* raw_span, int H, int W, int64_t pitch, int flags, int span_row0,
                                          int span_rows, uint8_t* out, int32_t* first_last, void* workspace,
                                          size_t workspace_bytes, void* stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  NBC_REQUIRE((raw_span || span_rows == 0) && out && first_last && workspace, "nbc_preprocess_4x_u8: null pointer");
-  NBC_REQUIRE(span_row0 >= 0 && span_rows >= 0 && span_row0 % 4 == 0 && span_rows % 4 == 0 && span_row0 + span_rows <= H,
-              "nbc_preprocess_4x_span_u8: the span [%d, +%d) must be made of whole groups of 4 rows inside the image", span_row0,
-              span_rows);
-  // the kernel addresses memory row r at raw + r * pitch and never touches a row outside the span
-  const uint8_t* raw = raw_span ? raw_span - (int64_t)span_row0 * pitch : reinterpret_cast<const uint8_t*>(workspace);
-  NBC_REQUIRE(H > 0 && W > 0 && H % 4 == 0 && W % 4 == 0, "nbc_preprocess_4x_u8: H and W must be multiples of 4 (got %dx%d)", H, W);
-  NBC_REQUIRE(pitch >= (int64_t)W * 3, "nbc_preprocess_4x_u8: pitch %lld < 3*W", (long long)pitch);
-  if (workspace_bytes < nbc_preprocess_workspace_bytes(H, W)) {
-    set_error("nbc_preprocess_4x_u8: workspace %zu < %zu", workspace_bytes, nbc_preprocess_workspace_bytes(H, W));
-    return NBC_ERR_WORKSPACE;
-  }
-  const int Ho = H / 4, Wo = W / 4;
-  char* ws = reinterpret_cast<char*>(workspace);
-  PreHeader* hdr = reinterpret_cast<PreHeader*>(ws);
-  int* rowcount = reinterpret_cast<int*>(ws + sizeof(PreHeader));
-  uint8_t* r8 = reinterpret_cast<uint8_t*>(ws + pre_header_bytes(H));     // saturated u8 intermediate, Ho x Wo x 3
-  NBC_CUDA(cudaMemsetAsync(ws, 0, sizeof(PreHeader) + (size_t)Ho * sizeof(int), stream));
-  const int groups = (Wo + 3) / 4;
-  dim3 grid(ceil_div(groups, 256), Ho);
-  const bool aligned = (reinterpret_cast<uintptr_t>(raw) % 16 == 0) && (pitch % 16 == 0);
-  if (aligned)
-    resize4x_pass1<true><<<grid, 256, 0, stream>>>(raw, H, W, pitch, flags, r8, hdr, rowcount, span_row0, span_row0 + span_rows);
-  else
-    resize4x_pass1<false><<<grid, 256, 0, stream>>>(raw, H, W, pitch, flags, r8, hdr, rowcount, span_row0, span_row0 + span_rows);
-  NBC_CHECK_LAUNCH();
-  trim_rows_kernel<<<1, 1024, 0, stream>>>(rowcount, hdr, Ho, Wo, Ho == Wo ? 1 : 0, first_last);
-  NBC_CHECK_LAUNCH();
-  const int64_t total16 = ceil_div64((int64_t)Ho * Wo * 3, 16);
-  const int blocks = (int)(total16 < 256 ? 1 : (ceil_div64(total16, 256) < 4 * 148 ? ceil_div64(total16, 256) : 4 * 148));
-  resize4x_pass2<<<blocks, 256, 0, stream>>>(r8, hdr, Wo, first_last, out);
-  NBC_CHECK_LAUNCH();
-  return 0;
+  const int32_t r0 = span_row0, rows = span_rows;
+  return preprocess_4x_batch(&raw_span, &r0, &rows, 1, H, W, pitch, flags, out, 0, first_last, workspace, workspace_bytes,
+                             reinterpret_cast<cudaStream_t>(stream_), "nbc_preprocess_4x_span_u8");
+}
+
+extern "C" int nbc_preprocess_4x_batch_u8(const uint8_t* const* raw_spans, const int32_t* span_row0, const int32_t* span_rows,
+                                          int n, int H, int W, int64_t pitch, int flags, uint8_t* out, int64_t out_stride_bytes,
+                                          int32_t* first_last, void* workspace, size_t workspace_bytes, void* stream_) {
+  NBC_REQUIRE(n > 0 && n <= 4096, "nbc_preprocess_4x_batch_u8: bad scan count %d", n);
+  NBC_REQUIRE(out_stride_bytes >= (int64_t)(H / 4) * (W / 4) * 3, "nbc_preprocess_4x_batch_u8: out stride smaller than one result");
+  return preprocess_4x_batch(raw_spans, span_row0, span_rows, n, H, W, pitch, flags, out, out_stride_bytes, first_last, workspace,
+                             workspace_bytes, reinterpret_cast<cudaStream_t>(stream_), "nbc_preprocess_4x_batch_u8");
 }
 
 extern "C" int nbc_trim_u8(const uint8_t* img, int H, int W, uint8_t* out, int32_t* first_last, void* workspace,

@@ -27,8 +27,9 @@ from . import ops
 # images per ragged batch: the per-launch cost of the 53 network kernels (launch gap, pipeline fill and drain, the last
 # partial wave) is amortised over the chunk -- 0.631 ms per image at 8, 0.608 at 12 (profiles/r01t_pdl_chunk_depth_sweep.txt)
 DEFAULT_CHUNK = 8
-# raw-scan staging buffers of the host path (50 MB each): the H2D stream runs this many scans ahead of K1
-DEFAULT_STAGE_DEPTH = 4
+# raw-scan staging buffers of the host path (50 MB each), in units of chunks: K1 runs once per chunk (three launches for all
+# its scans), so the H2D stream needs a second chunk's worth of buffers to keep copying while K1 waits for its turn
+DEFAULT_STAGE_DEPTH = 2
 
 
 class _Slot:
@@ -60,15 +61,15 @@ class PredictEngine:
     def __init__(self, model, device='cuda:0', threshold=150, raw_size=4096, chunk=None, depth=None):
         if chunk is None:
             chunk = int(os.environ.get('NBC_CHUNK', DEFAULT_CHUNK))
-        if depth is None:
-            depth = int(os.environ.get('NBC_STAGE_DEPTH', DEFAULT_STAGE_DEPTH))
+        if depth is None:      # staging buffers (NBC_STAGE_DEPTH counts chunks)
+            depth = int(os.environ.get('NBC_STAGE_DEPTH', DEFAULT_STAGE_DEPTH)) * chunk
         self.model = model
         self.device = torch.device(device)
         self.threshold = threshold
         self.raw_size = raw_size
         self.out_w = raw_size // 4
         self.chunk = chunk
-        self.depth = depth
+        self.depth = max(depth, chunk)      # a chunk's scans are all staged before its K1 runs
         self.zero_span = os.environ.get('NBC_ZERO_SPAN', '1') != '0'
         self._scan_pool = None
         self.h2d_bytes = 0        # raw-scan bytes really copied host -> device so far
@@ -107,7 +108,7 @@ class PredictEngine:
         self._staged = [torch.cuda.Event() for _ in range(self.depth)]
         self._freed = [torch.cuda.Event() for _ in range(self.depth)]
         lib = ops._lib.load()
-        self._pre_ws = torch.empty(lib.nbc_preprocess_workspace_bytes(S, S), dtype=torch.uint8, device=dev)
+        self._pre_ws = torch.empty(self.chunk * lib.nbc_preprocess_workspace_bytes(S, S), dtype=torch.uint8, device=dev)
         self._ccl_ws = torch.empty(lib.nbc_ccl_workspace_bytes(self.chunk, Hc, Wo), dtype=torch.uint8, device=dev)
         hl = (((Hc - 1) // 2 + 1 - 1) // 2 + 1 - 1) // 2 + 1
         wl = (((Wo - 1) // 2 + 1 - 1) // 2 + 1 - 1) // 2 + 1
@@ -126,6 +127,21 @@ class PredictEngine:
                                                      C.c_void_p(self._pre_ws.data_ptr()), self._pre_ws.numel(),
                                                      C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
                        'nbc_preprocess_4x_span_u8')
+
+    def _preprocess_chunk(self, slot, a, b, ptrs, spans, bgr, bottom_up):
+        """K1 for images a..b-1 of the slot in three launches (nbc_preprocess_4x_batch_u8) on the current stream.  ptrs: device
+        addresses of the (span of the) raw scans; spans: (row0, rows) per scan."""
+        lib = ops._lib.load()
+        S, n = self.raw_size, b - a
+        arr = (C.c_void_p * n)(*ptrs)
+        r0 = (C.c_int32 * n)(*[sp[0] for sp in spans])
+        rows = (C.c_int32 * n)(*[sp[1] for sp in spans])
+        ops._lib.check(lib.nbc_preprocess_4x_batch_u8(arr, r0, rows, n, S, S, S * 3, (1 if bgr else 0) | (2 if bottom_up else 0),
+                                                      C.c_void_p(slot.proc[a].data_ptr()), slot.proc.stride(0),
+                                                      C.c_void_p(slot.fl[a].data_ptr()), C.c_void_p(self._pre_ws.data_ptr()),
+                                                      self._pre_ws.numel(),
+                                                      C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
+                       'nbc_preprocess_4x_batch_u8')
 
     def _scan(self, raw):
         """(row0, rows) of a host scan: the memory rows between its all-zero bands, in whole groups of 4."""
@@ -199,6 +215,7 @@ class PredictEngine:
             span_of = None if on_device else self._spans(n, get_raw, spans)
             pitch = self.raw_size * 3
             for (a, b) in chunks:
+                ptrs, spans_ab, used = [], [], []
                 for i in range(a, b):
                     raw = get_raw(i)
                     if not raw.is_cuda:
@@ -209,16 +226,21 @@ class PredictEngine:
                                 self._copy_stream.wait_event(self._freed[k])
                             if rows:      # one cudaMemcpyAsync per scan: the rows between the dark bands
                                 self._stage[k][:rows * pitch].copy_(raw[row0 * pitch:(row0 + rows) * pitch], non_blocking=True)
-                            self._staged[k].record(self._copy_stream)
                         self.h2d_bytes += rows * pitch
-                        self._pre_stream.wait_event(self._staged[k])
-                        with torch.cuda.stream(self._pre_stream):
-                            self._preprocess_into(slot, i, self._stage[k], bgr, bottom_up, (row0, rows))
-                            self._freed[k].record(self._pre_stream)
+                        ptrs.append(self._stage[k].data_ptr())
+                        spans_ab.append((row0, rows))
+                        used.append(k)
                         self._issued += 1
                     else:
-                        with torch.cuda.stream(self._pre_stream):
-                            self._preprocess_into(slot, i, raw, bgr, bottom_up)
+                        ptrs.append(raw.data_ptr())
+                        spans_ab.append((0, self.raw_size))
+                if used:
+                    self._staged[used[-1]].record(self._copy_stream)      # the copy stream is in order: all of the chunk's copies
+                    self._pre_stream.wait_event(self._staged[used[-1]])
+                with torch.cuda.stream(self._pre_stream):
+                    self._preprocess_chunk(slot, a, b, ptrs, spans_ab, bgr, bottom_up)      # K1 for the whole chunk
+                    for k in used:
+                        self._freed[k].record(self._pre_stream)
                 pre_done = torch.cuda.Event()
                 with torch.cuda.stream(self._pre_stream):
                     ops.heights_from_first_last(slot.fl[a:b], out=slot.heights[a:b])

@@ -88,6 +88,29 @@ def preprocess_4x(raw, H, W, pitch=None, bgr=False, bottom_up=False, workspace=N
     return out, fl
 
 
+def preprocess_4x_batch(raws, H, W, spans=None, pitch=None, bgr=False, bottom_up=False):
+    """K1 for a chunk of scans of one size in three launches (nbc_preprocess_4x_batch_u8).  raws: list of u8 CUDA tensors
+    (whole pixel arrays, or only the rows of ``spans[i] = (row0, rows)``).  Returns (canvas u8 [n, H/4, W/4, 3] -- image i in
+    rows [0, last_i - first_i) --, first_last int32 [n, 2])."""
+    lib = _lib.load()
+    n = len(raws)
+    raws = [_contig(r, torch.uint8, 'raw') for r in raws]
+    dev = raws[0].device
+    pitch = W * 3 if pitch is None else pitch
+    spans = [(0, H)] * n if spans is None else list(spans)
+    with torch.cuda.device(dev):
+        ws = torch.empty(n * lib.nbc_preprocess_workspace_bytes(H, W), dtype=torch.uint8, device=dev)
+        out = torch.empty((n, H // 4, W // 4, 3), dtype=torch.uint8, device=dev)
+        fl = torch.empty((n, 2), dtype=torch.int32, device=dev)
+        arr = (C.c_void_p * n)(*[r.data_ptr() if r.numel() else None for r in raws])
+        r0 = (C.c_int32 * n)(*[s[0] for s in spans])
+        rows = (C.c_int32 * n)(*[s[1] for s in spans])
+        _lib.check(lib.nbc_preprocess_4x_batch_u8(arr, r0, rows, n, H, W, pitch, (1 if bgr else 0) | (2 if bottom_up else 0), _ptr(out),
+                                                  out.stride(0), _ptr(fl), _ptr(ws), ws.numel(), _stream(dev)),
+                   'nbc_preprocess_4x_batch_u8')
+    return out, fl
+
+
 def preprocess_general(raw, H, W, target=1024, pitch=None, bgr=False, bottom_up=False):
     """General-ratio variant of ``preprocess_4x``: any H x W pixel array -> target x target cubic resize + trim
     (models.py:194-203).  Returns (out u8 [target*target*3] flat buffer, first_last int32[2] CUDA tensor); the trimmed

@@ -119,6 +119,20 @@ def test_preprocess_zero_band_span(cuda_device):
             n = (fla[1] - fla[0]).item() * (W // 4) * 3
             assert torch.equal(a[:n], b[:n]), name
     assert rows == 0       # the last case really was the empty span
+    # the chunk entry (three launches for n scans, what the engine issues): whole scans, spans and an all-zero scan mixed
+    H = W = 512
+    imgs = [synth.raw_image_u8(seed=20 + i, size=H, top=t, bottom=b)[0] for i, (t, b) in enumerate(((57, 130), (4, 9), (200, 1)))]
+    imgs.append(np.zeros((H, W, 3), np.uint8))
+    srcs = [np.ascontiguousarray(im[::-1, :, ::-1]) for im in imgs]               # BMP order
+    spans = [ops.host_zero_row_span(s_, H, W * 3) for s_ in srcs]
+    spans[1] = (0, H)                                                             # one scan copied whole
+    parts = [torch.from_numpy(s_[r0:r0 + n].copy()).to(cuda_device).view(-1) for s_, (r0, n) in zip(srcs, spans)]
+    canvas, fl = ops.preprocess_4x_batch(parts, H, W, spans, bgr=True, bottom_up=True)
+    for i, s_ in enumerate(srcs):
+        a, fla = ops.preprocess_4x(torch.from_numpy(s_).to(cuda_device).view(-1), H, W, bgr=True, bottom_up=True)
+        assert fl[i].tolist() == fla.tolist(), i
+        n = (fla[1] - fla[0]).item() * (W // 4) * 3
+        assert torch.equal(canvas[i].view(-1)[:n], a[:n]), i
 
 
 def test_preprocess_general_ratio(cuda_device):

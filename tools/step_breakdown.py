@@ -48,9 +48,8 @@ def main():
             plan.forward_ragged(slot.proc[a:b], heights=slot.heights[a:b], out=logits[k][:b - a])
 
     def k1():
-        for i in range(n):
-            eng._preprocess_into(slot, i, raws[i], True, True)
         for (a, b) in chunks:
+            eng._preprocess_chunk(slot, a, b, [raws[i].data_ptr() for i in range(a, b)], [(0, eng.raw_size)] * (b - a), True, True)
             ops.heights_from_first_last(slot.fl[a:b], out=slot.heights[a:b])
 
     def k3():
