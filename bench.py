@@ -317,6 +317,7 @@ def main():
                     'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
                     'config': train_config(B, world),
                     'clocks': clocks, 'gpu_launches': launches, 'loss': float(res['loss']),
+                    'gradient_exchange': ('%d overlapped buckets' % len(tr.gradient_buckets())) if tr.bucket_mb > 0 else 'one all-reduce after the backward',
                     'e2e': {'value': world * B * args.steps / (ms_h / 1000.0), 'unit': 'images/s',
                             'h2d_bytes_per_step': int(imgs_h.numel() + tgt_h.numel()), 'd2h_bytes_per_step': 4,
                             'ms_per_step': ms_h / args.steps},

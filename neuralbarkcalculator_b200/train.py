@@ -4,12 +4,16 @@
 step in ``libnbc.so``: train-mode forward (batch-statistics BatchNorm, Dropout(0.8) in the head as
 ``fcn_resnet50(dropout=0.8)``), ``CustomWeightedCrossEntropy`` (utils.py:151-165), full backward, and Adam
 (lr 5e-4, L2 weight decay 2e-3 as ``__main__.py:234``).  Data parallel: one process per GPU, the flat gradient buffer is
-all-reduced over NCCL (``torch.distributed``) between backward and the optimiser -- the only collective of the path --
-in BUCKETS that start while the backward is still running: the native backward records an event each time a segment of
-the gradient buffer (head, then the bottleneck blocks last to first, then the stem) is final, consecutive segments are
-merged into buckets of >= ``bucket_mb`` and each bucket's all-reduce is enqueued on a side stream behind its event
-(``NBC_TRAIN_BUCKETS=0`` or ``bucket_mb=0``: one all-reduce after the backward).  Adam waits for all of them.
-No torch autograd, no torch ops on the data path."""
+all-reduced over NCCL (``torch.distributed``) between backward and the optimiser -- the only collective of the path.
+Two modes: ONE all-reduce after the backward (the default: 132 MB over NVLink 5 / NVSwitch takes about half a
+millisecond of a 47 ms step), or BUCKETS that start while the backward is still running (``bucket_mb > 0`` /
+``NBC_TRAIN_BUCKETS=1``): the native backward records an event each time a segment of the gradient buffer (head, then
+the bottleneck blocks last to first, then the stem) is final, consecutive segments are merged into buckets of
+>= ``bucket_mb`` and each bucket's all-reduce is enqueued on a side stream behind its event; Adam waits for all of them.
+Measured on 8 B200 (profiles/r02c_bench_train_g8*.json): 1 336 img/s with the single all-reduce (97.4 % of 8 x one GPU),
+1 318 with 7 overlapped buckets -- an NCCL kernel that starts in the middle of the backward takes SMs away from the
+persistent convolution kernels, which need all 148, and that costs more than the exposed half millisecond; hence the
+default.  No torch autograd, no torch ops on the data path."""
 import ctypes as C
 import os
 
@@ -49,7 +53,7 @@ def merge_segments(segments, min_bytes):
 class Trainer:
     def __init__(self, state_dict, N, H, W, device='cuda:0', lr=5e-4, weight_decay=2e-3, betas=(0.9, 0.999), eps=1e-8,
                  dropout=0.8, class_weights=None, mean=(0.7399, 0.6139, 0.4401), std=(0.1068, 0.1272, 0.1271),
-                 loss='weighted_ce', bucket_mb=16.0, seed=0):
+                 loss='weighted_ce', bucket_mb=0.0, seed=0):
         self.lib = _lib.load()
         self.device = torch.device(device)
         _lib.require_device(self.device.index if self.device.index is not None else torch.cuda.current_device())
@@ -59,8 +63,9 @@ class Trainer:
         self.std3 = (C.c_float * 3)(*std)
         self.step_count = 0
         self.base_seed = int(seed)
-        if os.environ.get('NBC_TRAIN_BUCKETS', '1') == '0':
-            bucket_mb = 0.0
+        env = os.environ.get('NBC_TRAIN_BUCKETS')
+        if env is not None and env != '':      # 0: single all-reduce; 1: 16 MB buckets; any other number: that many MB
+            bucket_mb = 0.0 if env == '0' else (16.0 if env == '1' else float(env))
         self.bucket_mb = float(bucket_mb)
         self._buckets = None
         self._comm_stream = None
