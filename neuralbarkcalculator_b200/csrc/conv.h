@@ -45,8 +45,9 @@ int stem_tc_pad(const void* input, int input_kind, int N, int H, int W, const fl
                 cudaStream_t stream, const int* valid_h, int f16 = 0);
 int maxpool_ragged(const void* x, int N, int H, int W, int C, void* y, const int* valid_h, cudaStream_t stream,
                    int f16 = 0);
+// valid_h (optional, ragged batch): rows of image n at or beyond valid_h[n] are skipped; row_w = pixels per row
 int head_1x1(const void* x16, int64_t pixels_per_image, int N, int Cin, const float* w3xC, const float* bias3,
-             float* logits_planar, int f16, cudaStream_t stream);
+             float* logits_planar, int f16, cudaStream_t stream, const int* valid_h = nullptr, int row_w = 1);
 // levels[4][N]: valid rows per image at full, 1/2, 1/4 and 1/8 resolution, from heights[N] or K1's {first,last}[N]
 int ragged_levels(const int* heights, const int* first_last, int N, int Hc, int* levels, cudaStream_t stream);
 

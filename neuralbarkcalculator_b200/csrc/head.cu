@@ -16,7 +16,8 @@ namespace nbc {
 template <int kIters>
 __global__ void __launch_bounds__(256) head1x1_kernel(const __nv_bfloat16* __restrict__ x, int64_t P, int N, int Cin,
                                                       const float* __restrict__ w, const float* __restrict__ bias,
-                                                      float* __restrict__ logits, int f16) {
+                                                      float* __restrict__ logits, int f16, const int* __restrict__ valid_h,
+                                                      int row_w) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -30,6 +31,10 @@ __global__ void __launch_bounds__(256) head1x1_kernel(const __nv_bfloat16* __res
 #pragma unroll
       for (int e = 0; e < 8; ++e) wr[it][k][e] = __ldg(w + k * Cin + it * 256 + lane * 8 + e);
   for (int64_t m = warp_global; m < M; m += nwarps) {
+    if (valid_h != nullptr) {      // ragged batch: rows at or below an image's last valid one feed nothing (K3 clamps its taps)
+      const int64_t img = m / P;
+      if ((m - img * P) / row_w >= __ldg(valid_h + img)) continue;
+    }
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     const __nv_bfloat16* xr = x + m * Cin + lane * 8;
     uint4 v[kIters];
@@ -209,7 +214,7 @@ extern "C" int nbc_upsample_argmax_ragged(const float* logits, int N, int hc, in
 
 namespace nbc {
 int head_1x1(const void* x_bf16, int64_t pixels_per_image, int N, int Cin, const float* w3xC, const float* bias3,
-             float* logits_planar, int f16, cudaStream_t stream) {
+             float* logits_planar, int f16, cudaStream_t stream, const int* valid_h, int row_w) {
   NBC_REQUIRE(x_bf16 && w3xC && bias3 && logits_planar, "nbc_head_1x1: null pointer");
   NBC_REQUIRE((Cin == 256 || Cin == 512 || Cin == 1024) && N > 0 && pixels_per_image > 0,
               "nbc_head_1x1: Cin must be 256, 512 or 1024 (got %d)", Cin);
@@ -218,11 +223,11 @@ int head_1x1(const void* x_bf16, int64_t pixels_per_image, int N, int Cin, const
   const int blocks = (int)(want < 148 * 8 ? (want < 1 ? 1 : want) : 148 * 8);
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x_bf16);
   if (Cin == 256)
-    head1x1_kernel<1><<<blocks, 256, 0, stream>>>(xb, pixels_per_image, N, Cin, w3xC, bias3, logits_planar, f16);
+    head1x1_kernel<1><<<blocks, 256, 0, stream>>>(xb, pixels_per_image, N, Cin, w3xC, bias3, logits_planar, f16, valid_h, row_w);
   else if (Cin == 512)
-    head1x1_kernel<2><<<blocks, 256, 0, stream>>>(xb, pixels_per_image, N, Cin, w3xC, bias3, logits_planar, f16);
+    head1x1_kernel<2><<<blocks, 256, 0, stream>>>(xb, pixels_per_image, N, Cin, w3xC, bias3, logits_planar, f16, valid_h, row_w);
   else
-    head1x1_kernel<4><<<blocks, 256, 0, stream>>>(xb, pixels_per_image, N, Cin, w3xC, bias3, logits_planar, f16);
+    head1x1_kernel<4><<<blocks, 256, 0, stream>>>(xb, pixels_per_image, N, Cin, w3xC, bias3, logits_planar, f16, valid_h, row_w);
   NBC_CHECK_LAUNCH();
   return 0;
 }
@@ -231,7 +236,7 @@ int head_1x1(const void* x_bf16, int64_t pixels_per_image, int N, int Cin, const
 extern "C" int nbc_head_1x1(const void* x_bf16, int64_t pixels_per_image, int N, int Cin, int f16, const float* w3xC,
                             const float* bias3, float* logits_planar, void* stream) {
   return head_1x1(x_bf16, pixels_per_image, N, Cin, w3xC, bias3, logits_planar, f16 ? 1 : 0,
-                  reinterpret_cast<cudaStream_t>(stream));
+                  reinterpret_cast<cudaStream_t>(stream), nullptr, 1);
 }
 
 static int upsample_common(const float* logits, int N, int C, int h, int w, int H, int W, uint8_t* mask, float* out,

@@ -256,7 +256,8 @@ static int build_steps(nbc_plan* p, int N, int H, int W, void* workspace, bool r
   Step s;
   memset(&s.prep, 0, sizeof(s.prep));
   s.kind = 4, s.g = ConvGeom{N, hh, wh, 512, 3, 1, 1, 1, 0, 1, 0}, s.x = t1, s.y = logits, s.name = "head1x1";
-  s.w = p->cls_w, s.bias = p->cls_b, s.residual = nullptr;
+  s.w = p->cls_w, s.bias = p->cls_b;
+  s.residual = levels != nullptr ? levels + (size_t)3 * N : nullptr;      // ragged: valid rows at 1/8 resolution
   steps.push_back(s);
   return 0;
 }
@@ -284,7 +285,8 @@ static int run_step(nbc_plan* p, const Step& s, const void* input, int input_kin
     case 2: return conv_tc_run(&s.prep, stream);
     case 3: return conv_mma(s.g, s.x, s.w, s.bias, s.residual, s.y, stream);
     case 4:
-      return head_1x1(s.x, (int64_t)s.g.H * s.g.W, s.g.N, 512, p->cls_w, p->cls_b, logits, p->f16, stream);
+      return head_1x1(s.x, (int64_t)s.g.H * s.g.W, s.g.N, 512, p->cls_w, p->cls_b, logits, p->f16, stream,
+                      reinterpret_cast<const int*>(s.residual), s.g.W);
   }
   return NBC_ERR_INVALID;
 }

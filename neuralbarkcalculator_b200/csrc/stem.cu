@@ -111,6 +111,9 @@ __global__ void __launch_bounds__(256) stem_pad_kernel(const StemParams p, int H
     const int img = (int)(t / Hp);
     float v[3] = {0.f, 0.f, 0.f};
     const int vh = valid_h ? min(p.H, __ldg(valid_h + img)) : p.H;   // ragged batch: rows >= vh are zero padding
+    // ... of which the stem reads at most the 7-row window of its last valid output row (2 * ceil(vh / 2) + 3 < vh + 5);
+    // the dead part of the canvas below is never read and need not be written
+    if (valid_h && y >= vh + 8) continue;
     if (y >= 0 && y < vh && x >= 0 && x < p.W) {
       if (kF32) {
 #pragma unroll
