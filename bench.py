@@ -366,7 +366,7 @@ def main():
             v = B * len(times) / sum(times)
             print(json.dumps({'metric': 'images/sec (predict.py CLI, files in, files out)', 'value': v, 'unit': 'images/s', 'n_gpus': 1,
                               'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * sum(times) / len(times),
-                              'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+                              'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
                               'config': {'workload': 'predict.py ROOT --exclude_nodes on %d synthetic 4096x4096 24-bit BMPs on tmpfs: '
                                                      'BMP read, K1, FCN-ResNet50, K3, K5, processed + dual PNG encode, CSV (configs[1]); '
                                                      'includes model construction and weight packing each step' % B,
@@ -477,7 +477,7 @@ def main():
         achieved = conv_fl / (conv_ms * 1e-3) / 1e12
         traffic, tensor_pct, ncu_src = None, None, None
         tp = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')     # dram bytes per launch from the committed ncu capture
-        if os.path.exists(tp):
+        if os.path.exists(tp) and kind == 'predict64':      # the capture is of this workload's representative launch set
             tj = json.load(open(tp))
             traffic = tj.get('conv_tc_dram_bytes_per_launch')
             tensor_pct = tj.get('conv_tc_tensor_pipe_active_pct_time_weighted')
