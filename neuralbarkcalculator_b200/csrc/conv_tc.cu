@@ -1020,6 +1020,220 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_stem_kernel(const __gri
   if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// 3x3 HALO kernel for the 64 -> 64 convolutions of layer1 (stride 1, dilation 1, pad 1; 128 x 1 output tiles).
+// conv_tc_kernel fetches the A operand of every tap as its own shifted 128-pixel box: nine L2 fetches of every input
+// byte, and ncu shows those launches bound by that request rate (24.7 % tensor-pipe activity at 0.9 TB/s of DRAM traffic).
+// Here ONE TMA box per tile -- {64 ch, 130 px, 3 rows} of the NHWC input starting one pixel up and left of the tile, the
+// conv padding zero-filled by the TMA unit -- lands as 390 rows of 128 bytes in the 128-byte-swizzled K-major layout, and
+// tap (ky, kx) is the very same tile read through a descriptor whose start address is advanced by (130 ky + kx) rows.
+// A start address that is not a multiple of the 1024-byte swizzle atom needs the descriptor's BASE OFFSET field
+// ((start >> 7) & 7: the phase of the swizzle pattern at the first row).  The nine 8 KB weight slabs stay resident in
+// shared memory for the whole kernel.  Epilogue / output path as in conv_tc_kernel<64, ...>.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kHaloW = 130;
+constexpr int kHaloStageBytes = 50176;               // 3 x 130 x 128 B = 49 920, rounded up to 49 x 1024
+constexpr int kHaloStages = 2;
+constexpr int kHaloOB = 3;
+constexpr int kHaloWBytes = 9 * 64 * 128;            // 9 taps x 64 output channels x 64 input channels x 2 B
+constexpr int kHaloSmemBytes = kHaloStages * kHaloStageBytes + kHaloWBytes + kHaloOB * kOutBufBytes + 256 + kMapBytes + 1024;
+static_assert(kHaloSmemBytes <= kSmemLimit && kHaloSmemBytes > 120 * 1024, "3x3 halo kernel: shared memory budget");
+
+// 128B-swizzled K-major descriptor whose start address may sit anywhere inside a swizzle atom (see above)
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128_at(uint32_t smem_addr) {
+  return umma_desc_kmajor<128>(smem_addr) | ((uint64_t)((smem_addr >> 7) & 7u) << 49);
+}
+
+template <bool RELU, bool F16>
+__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_halo3_kernel(const __grid_constant__ ConvTcParams p) {
+  constexpr int BN = 64, OB = kHaloOB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wres = smem + kHaloStages * kHaloStageBytes;      // resident weights, 1024-aligned
+  uint8_t* obuf = wres + kHaloWBytes;                        // OB staging buffers, 1024-aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(obuf + OB * kOutBufBytes);
+  uint64_t* empty_bar = full_bar + kHaloStages;
+  uint64_t* tfull_bar = empty_bar + kHaloStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* bufready_bar = tempty_bar + 2;
+  uint64_t* outready_bar = bufready_bar + OB;
+  uint64_t* w_bar = outready_bar + OB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kHaloStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);
+    }
+    for (int i = 0; i < OB; ++i) {
+      mbar_init(&bufready_bar[i], 1);
+      mbar_init(&outready_bar[i], 8);
+    }
+    mbar_init(w_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA[1]);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 10 && lane == 0) tma_prefetch_desc(&p.tmOut);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  pdl_launch_dependents();
+  pdl_wait();
+
+  int* s_map_mem = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
+  const int* s_map = ragged_map_setup(p, s_map_mem) ? s_map_mem : nullptr;
+  const int total_tiles = s_map ? s_map[p.N] : p.num_m_tiles;      // one N tile: all 64 output channels
+
+  if (warp == 0) {
+    // ================================ producer: weights once, then one halo box per tile ================================
+    if (elect_one()) {
+      mbar_expect_tx(w_bar, kHaloWBytes);
+      for (int t = 0; t < 9; ++t) tma_load_2d(wres + t * 8192, &p.tmB, w_bar, t * 64, 0);
+      uint32_t stage = 0, phase = 0;
+      int hint = 0;
+      for (int vt = blockIdx.x; vt < total_tiles; vt += gridDim.x) {
+        const VTile v = vtile(p, s_map, vt, hint);
+        if (v.dead) continue;
+        mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + (int)stage);
+        mbar_expect_tx(&full_bar[stage], 3 * kHaloW * 128);
+        tma_load_4d(smem + stage * kHaloStageBytes, &p.tmA[1], &full_bar[stage], 0, v.t.w0 - 1, v.t.h0 - 1, v.t.img);
+        if (++stage == kHaloStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (elect_one()) {
+      constexpr uint32_t idesc = F16 ? umma_idesc_f16(128, BN) : umma_idesc_bf16(128, BN);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      mbar_wait(w_bar, 0, 700);
+      const uint32_t w_addr = smem_u32(wres);
+      int hint = 0;
+      for (int vt = blockIdx.x; vt < total_tiles; vt += gridDim.x) {
+        if (vtile(p, s_map, vt, hint).dead) continue;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 300 + (int)acc);
+        mbar_wait(&full_bar[stage], phase, 200 + (int)stage);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t a_addr = smem_u32(smem + stage * kHaloStageBytes);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const uint32_t a_tap = a_addr + (uint32_t)((t / 3) * kHaloW + (t % 3)) * 128u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16(d_tmem, umma_desc_kmajor_sw128_at(a_tap + k * 32), umma_desc_kmajor<128>(w_addr + t * 8192 + k * 32), idesc,
+                      (uint32_t)((t | k) != 0));
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&tfull_bar[acc]);
+        if (++stage == kHaloStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 10) {
+    // ================================ output TMA ================================
+    if (elect_one()) {
+      uint32_t st_s = 0;
+      int hint = 0;
+      for (int vt = blockIdx.x; vt < total_tiles; vt += gridDim.x) {
+        const VTile v = vtile(p, s_map, vt, hint);
+        if (v.dead) continue;
+        const uint32_t b = st_s % OB;
+        mbar_wait(&outready_bar[b], (st_s / OB) & 1u, 500 + (int)b);
+        tma_store_4d(&p.tmOut, obuf + b * kOutBufBytes, 0, v.t.w0, v.t.h0, v.t.img);
+        tma_store_commit();
+        tma_store_wait_read<0>();
+        mbar_arrive(&bufready_bar[b]);
+        ++st_s;
+      }
+      tma_store_wait_all();
+    }
+    __syncwarp();
+  } else {
+    // ================================ epilogue (warps 2..9): as conv_tc_kernel with BN = 64 ================================
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;            // which 32 of the 64 columns
+    const int row = q * 32 + lane;
+    const uint32_t row_off = (uint32_t)row * 128u;
+    const uint32_t rsw = (uint32_t)(row & 7);
+    const int u0 = half * 4;
+    uint32_t acc = 0, acc_phase = 0, live_tiles = 0;
+    int hint = 0;
+    for (int vt = blockIdx.x; vt < total_tiles; vt += gridDim.x) {
+      const TileCoord t = vtile(p, s_map, vt, hint).t;
+      const int vh = p.valid_h != nullptr ? __ldg(p.valid_h + t.img) : INT_MAX;
+      const int h = t.h0, w = t.w0 + row;
+      if (t.h0 >= vh) {
+        if (t.h0 < vh + kRaggedHalo && w < p.Wo && h < p.Ho) {
+          __nv_bfloat16* o = p.out + (((int64_t)t.img * p.Ho + h) * p.Wo + w) * p.Cout + half * 32;
+          for (int c = 0; c < 32; c += 8) *reinterpret_cast<uint4*>(o + c) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        continue;
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase, 400 + (int)acc);
+      tc_fence_after();
+      const uint32_t s = live_tiles;
+      const uint32_t b = s % OB;
+      uint32_t a[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + u0 * 8, a);
+      const float* bptr = p.bias + u0 * 8;
+      mbar_wait(&bufready_bar[b], ((s / OB) & 1u) ^ 1u, 600 + (int)b);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      uint8_t* rowp = obuf + b * kOutBufBytes + row_off;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bptr + u * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bptr + u * 8 + 4));
+        float v[8] = {__uint_as_float(a[u * 8 + 0]) + b0.x, __uint_as_float(a[u * 8 + 1]) + b0.y,
+                      __uint_as_float(a[u * 8 + 2]) + b0.z, __uint_as_float(a[u * 8 + 3]) + b0.w,
+                      __uint_as_float(a[u * 8 + 4]) + b1.x, __uint_as_float(a[u * 8 + 5]) + b1.y,
+                      __uint_as_float(a[u * 8 + 6]) + b1.z, __uint_as_float(a[u * 8 + 7]) + b1.w};
+        if (RELU) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+        }
+        *reinterpret_cast<uint4*>(rowp + ((((uint32_t)(u0 + u)) ^ rsw) << 4)) =
+            make_uint4(pack16x2(v[0], v[1], F16), pack16x2(v[2], v[3], F16), pack16x2(v[4], v[5], F16), pack16x2(v[6], v[7], F16));
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&outready_bar[b]);
+      ++live_tiles;
+      acc ^= 1u;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
@@ -1101,6 +1315,7 @@ struct ConvTcLaunch {
   int out_bufs;
   int pair;   // 1: conv_tc_pair_kernel (clusters of 2, cta_group::2 MMA)
   int stem_halo;   // 1: conv_tc_stem_kernel (halo tile; default where the tile geometry allows)
+  int halo3;       // 1: conv_tc_halo3_kernel (64 -> 64 3x3 out of one halo box per tile)
 };
 
 // Which launches run on CTA pairs (conv_tc_pair_kernel).  Measured per layer class on B200 (profiles/r01s_*): pairs win
@@ -1241,7 +1456,21 @@ static int build_launch(const ConvGeom& g, const void* x, const void* w, const f
     if (!used[0]) p.tmA[0] = p.tmA[p.tap_map[0]];
   }
   L->stem_halo = 0;
-  L->pair = want_pair(residual != nullptr ? 2 : (p.n_taps > 1 ? 4 : 1), bn, p.n_taps * p.cblocks);
+  // 3x3 halo kernel (layer1's 64 -> 64 convolutions): NBC_HALO3=0 keeps the nine-box path
+  static const int halo3 = [] {
+    const char* e = getenv("NBC_HALO3");
+    return (e && *e) ? atoi(e) : 1;
+  }();
+  L->halo3 = (halo3 == 1 && g.Cin == 64 && g.Cout == 64 && g.kh == 3 && g.kw == 3 && g.stride == 1 && g.dil == 1 && g.pad == 1 &&
+              residual == nullptr && p.tw == 128 && p.th == 1)
+                 ? 1
+                 : 0;
+  if (L->halo3) {
+    int rc = encode_act_map(&p.tmA[1], xb, g.Cin, g.W, g.H, g.N, (uint64_t)g.Cin * eb, (uint64_t)g.W * g.Cin * eb,
+                            (uint64_t)g.H * g.W * g.Cin * eb, kHaloW, 3);
+    if (rc) return rc;
+  }
+  L->pair = L->halo3 ? 0 : want_pair(residual != nullptr ? 2 : (p.n_taps > 1 ? 4 : 1), bn, p.n_taps * p.cblocks);
   int rc = encode_weight_map(&p.tmB, w, (uint64_t)p.n_taps * g.Cin, g.Cout, L->pair ? bn / 2 : bn);
   if (rc) return rc;
   rc = encode_out_maps(&p, g.N, Ho, Wo, g.Cout, y, residual);
@@ -1339,6 +1568,22 @@ static int launch_stem(const ConvTcLaunch& L, cudaStream_t stream) {
   return L.p.f16 ? launch_stem_one<false, true>(L, stream) : launch_stem_one<false, false>(L, stream);
 }
 
+template <bool RELU, bool F16>
+static int launch_halo3_one(const ConvTcLaunch& L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    NBC_CUDA(cudaFuncSetAttribute(conv_tc_halo3_kernel<RELU, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemBytes));
+    attr_set = true;
+  }
+  NBC_CUDA(launch_tc(conv_tc_halo3_kernel<RELU, F16>, L, kHaloSmemBytes, stream));
+  count_launch();
+  return 0;
+}
+static int launch_halo3(const ConvTcLaunch& L, cudaStream_t stream) {
+  if (L.p.relu) return L.p.f16 ? launch_halo3_one<true, true>(L, stream) : launch_halo3_one<true, false>(L, stream);
+  return L.p.f16 ? launch_halo3_one<false, true>(L, stream) : launch_halo3_one<false, false>(L, stream);
+}
+
 template <int BN, int KBLK>
 static int launch_bn(const ConvTcLaunch& L, cudaStream_t stream) {
   const bool res = L.p.residual != nullptr;
@@ -1392,6 +1637,7 @@ int conv_tc_prepare_stem(int N, int Ho, int Wo, int Hp, int Wp, const void* padd
   if (rc) return rc;
   L->out_bufs = 4;
   L->pair = 0;
+  L->halo3 = 0;
   // halo kernel (conv_tc_stem_kernel): 128 x 1 tiles only (the production geometry, Wo = 512); verified on B200 in round 2
   // (stem 0.180 -> 0.105 ms per [8,624,1024] pass) and the default since; NBC_STEM_HALO=0 selects the per-window kernel
   static const int halo = [] {
@@ -1466,6 +1712,7 @@ int conv_tc_prepare_dual(const ConvGeom& g, const void* x, const ConvGeom& g2, c
 int conv_tc_run(const ConvTcPrepared* prep, cudaStream_t stream) {
   const ConvTcLaunch* L = reinterpret_cast<const ConvTcLaunch*>(prep->storage);
   if (L->kblk == 32 && L->stem_halo) return launch_stem(*L, stream);
+  if (L->halo3) return launch_halo3(*L, stream);
   if (L->kblk == 32) return launch_bn<64, 32>(*L, stream);
   if (L->pair) return L->block_n == 256 ? launch_pair<256>(*L, stream) : launch_pair<128>(*L, stream);
   switch (L->block_n) {

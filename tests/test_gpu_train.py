@@ -112,6 +112,66 @@ def test_train_step_matches_oracle(cuda_device, synthetic_sd, weights):
     assert agree / total > (0.7 if strict else 0.55)
 
 
+def test_train_forward_every_unit_teacher_forced(cuda_device, synthetic_sd):
+    """TIGHT parity of the train-mode forward, unit by unit, at the full depth of the network: every convolution and every
+    batch-statistics BatchNorm (+ residual add + ReLU) is recomputed in torch f32 from the kernel's OWN stored input of that
+    unit (teacher forcing), so the layer-to-layer error amplification of a random-init train-mode network -- the reason
+    the end-to-end comparison above needs loose bounds -- never enters: what remains is one bf16 rounding per stored value."""
+    import torch.nn.functional as F
+    from neuralbarkcalculator_b200.train import Trainer
+    N, H, W = 2, 64, 96
+    imgs, tgt, x = _batch(N, H, W, seed=5)
+    sd = synthetic_sd
+    tr = Trainer(sd, N, H, W, device='cuda:0', dropout=0.0, class_weights=torch.ones(3))
+    tr.forward_backward(torch.from_numpy(imgs).to(cuda_device), torch.from_numpy(tgt).to(cuda_device), seed=1)
+    torch.cuda.synchronize()
+
+    def nchw(t):      # bf16 NHWC debug view -> f32 NCHW on the CPU
+        return t.float().cpu().permute(0, 3, 1, 2).contiguous()
+
+    def close(got, ref, what):      # one bf16 rounding of the stored value (2^-9 relative) + f32 summation-order noise
+        err = (got - ref).abs()
+        tol = 2.0 ** -7 * ref.abs() + 2e-3 * ref.abs().max()
+        assert (err <= tol).all(), '%s: max err %.4g at |ref| %.4g (max |ref| %.4g)' % (
+            what, err.max(), ref.flatten()[err.argmax()].abs(), ref.abs().max())
+
+    def check(unit, conv_key, bn_key, xin, stride, pad, dil, relu, residual=None):
+        w = sd[conv_key + '.weight'].to(torch.bfloat16).float()
+        z = nchw(tr.debug_tensor(0, unit))
+        close(z, F.conv2d(xin, w, stride=stride, padding=pad, dilation=dil), '%s z' % conv_key)
+        mean, var = z.mean((0, 2, 3), keepdim=True), z.var((0, 2, 3), unbiased=False, keepdim=True)
+        y_ref = (z - mean) / torch.sqrt(var + 1e-5) * sd[bn_key + '.weight'].view(1, -1, 1, 1) + sd[bn_key + '.bias'].view(1, -1, 1, 1)
+        if residual is not None:
+            y_ref = y_ref + residual
+        if relu:
+            y_ref = y_ref.relu()
+        y = nchw(tr.debug_tensor(1, unit))
+        close(y, y_ref, '%s y' % bn_key)
+        return y
+
+    xn = x.to(torch.bfloat16).float()      # the staging pass stores the normalised image in bf16
+    y = check(0, 'backbone.conv1', 'backbone.bn1', xn, 2, 3, 1, True)
+    cur = F.max_pool2d(y, 3, 2, 1)
+    unit, dil = 1, 1
+    for li, (nb, stride, dilate) in enumerate(((3, 1, False), (4, 2, False), (6, 1, True), (3, 1, True)), start=1):
+        for b in range(nb):
+            pre = 'backbone.layer%d.%d.' % (li, b)
+            s_ = stride if (b == 0 and not dilate) else 1
+            prev = dil
+            if b == 0 and dilate:
+                dil *= 2
+            d2 = prev if b == 0 else dil
+            a1 = check(unit, pre + 'conv1', pre + 'bn1', cur, 1, 0, 1, True)
+            a2 = check(unit + 1, pre + 'conv2', pre + 'bn2', a1, s_, d2, d2, True)
+            skip = cur
+            if b == 0:
+                skip = check(unit + 3, pre + 'downsample.0', pre + 'downsample.1', cur, s_, 0, 1, False)
+            cur = check(unit + 2, pre + 'conv3', pre + 'bn3', a2, 1, 0, 1, True, residual=skip)
+            unit += 4 if b == 0 else 3
+    check(unit, 'classifier.0', 'classifier.1', cur, 1, 1, 1, True)
+    assert unit + 1 == tr.lib.nbc_train_num_units(C.c_void_p(tr.handle))
+
+
 def test_train_gradients_strict_on_tamed_network(cuda_device, synthetic_sd):
     """Strict check of every backward kernel.  Shrinking gamma of the last BN of each bottleneck (x0.05) makes the
     residual branches small perturbations of the identity trunk, which removes the layer-to-layer error amplification
