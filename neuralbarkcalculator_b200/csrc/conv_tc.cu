@@ -1027,10 +1027,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_stem_kernel(const __gri
 // byte, and ncu shows those launches bound by that request rate (24.7 % tensor-pipe activity at 0.9 TB/s of DRAM traffic).
 // Here ONE TMA box per tile -- {64 ch, 130 px, 3 rows} of the NHWC input starting one pixel up and left of the tile, the
 // conv padding zero-filled by the TMA unit -- lands as 390 rows of 128 bytes in the 128-byte-swizzled K-major layout, and
-// tap (ky, kx) is the very same tile read through a descriptor whose start address is advanced by (130 ky + kx) rows.
-// A start address that is not a multiple of the 1024-byte swizzle atom needs the descriptor's BASE OFFSET field
-// ((start >> 7) & 7: the phase of the swizzle pattern at the first row).  The nine 8 KB weight slabs stay resident in
+// tap (ky, kx) is the very same tile read through a descriptor whose start address is advanced by (130 ky + kx) rows of
+// 128 bytes -- i.e. to an address that is NOT a multiple of the 1024-byte swizzle atom.  Measured on B200 (round 2, GPU
+// call 13): that works as is, with the descriptor's base-offset field left 0 -- the tensor core applies the 128-byte
+// swizzle to the absolute shared-memory address (bits [4,7) ^= bits [7,10)), exactly as the TMA unit did when it wrote
+// the tile; setting base offset = (start >> 7) & 7 gives wrong results.  The nine 8 KB weight slabs stay resident in
 // shared memory for the whole kernel.  Epilogue / output path as in conv_tc_kernel<64, ...>.
+// layer1 conv2: 0.049 -> 0.033 ms per [8,624,1024] pass (480 -> 715 TFLOP/s); NBC_HALO3=0 selects the nine-box path.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kHaloW = 130;
 constexpr int kHaloStageBytes = 50176;               // 3 x 130 x 128 B = 49 920, rounded up to 49 x 1024
@@ -1040,10 +1043,6 @@ constexpr int kHaloWBytes = 9 * 64 * 128;            // 9 taps x 64 output chann
 constexpr int kHaloSmemBytes = kHaloStages * kHaloStageBytes + kHaloWBytes + kHaloOB * kOutBufBytes + 256 + kMapBytes + 1024;
 static_assert(kHaloSmemBytes <= kSmemLimit && kHaloSmemBytes > 120 * 1024, "3x3 halo kernel: shared memory budget");
 
-// 128B-swizzled K-major descriptor whose start address may sit anywhere inside a swizzle atom (see above)
-__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128_at(uint32_t smem_addr) {
-  return umma_desc_kmajor<128>(smem_addr) | ((uint64_t)((smem_addr >> 7) & 7u) << 49);
-}
 
 template <bool RELU, bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_halo3_kernel(const __grid_constant__ ConvTcParams p) {
@@ -1136,7 +1135,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_halo3_kernel(const __gr
           const uint32_t a_tap = a_addr + (uint32_t)((t / 3) * kHaloW + (t % 3)) * 128u;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            umma_bf16(d_tmem, umma_desc_kmajor_sw128_at(a_tap + k * 32), umma_desc_kmajor<128>(w_addr + t * 8192 + k * 32), idesc,
+            umma_bf16(d_tmem, umma_desc_kmajor<128>(a_tap + k * 32), umma_desc_kmajor<128>(w_addr + t * 8192 + k * 32), idesc,
                       (uint32_t)((t | k) != 0));
           }
         }
