@@ -5,13 +5,15 @@
 
 workload predict64 (default, BASELINE.json configs[1]): a "step" is one pass of the predict hot path over a batch
 of 64 synthetic raw 4096x4096x3 scans (BMP pixel arrays: BGR, bottom-up, dark bands) with --exclude_nodes:
-K1 resize+trim -> FCN-ResNet50 (bf16, tcgen05) -> K3 upsample+argmax -> K5 region removal + class counts.
+K1 resize+trim -> FCN-ResNet50 (fp16 storage by default, tcgen05) -> K3 upsample+argmax -> K5 region removal + class counts.
   value : images/s, raw scans resident in HBM when the timed region starts (3.2 GB per rank, >> the 126 MB L2)
   e2e   : images/s through PredictEngine.submit_host / collect (the two halves of run_host): pinned host buffers in
-          (50 MB H2D per image, inside the timed region), masks + counts copied back to pinned host memory and
-          collected every step; step k+1 is submitted before step k is collected, as a folder-sized predict run does,
-          so the PCIe link (the end-to-end bound) stays busy across steps
-workload batch32 (configs[2]): model-only, u8 [32,1024,1024,3] -> mask + counts.
+          (inside the timed region; the engine copies only the rows between a scan's all-zero dark bands and counts the
+          bytes it copies -> h2d_bytes_per_step), masks + counts copied back to pinned host memory and collected every
+          step; step k+1 is submitted before step k is collected, as a folder-sized predict run does
+  roofline : the tensor-core conv launches of one network pass, per-launch CUDA events, against the BURST 16-bit peak (they
+          are timed alone); roofline.whole_step = algorithmic conv FLOPs of the step / ms_per_step against the SUSTAINED peak
+workload batch32 (configs[2]): model-only at 1024^2, u8 [32,1024,1024,3] -> mask + counts (e2e: images from / masks to pinned memory).
 workload train (configs[3]): one training step (train-mode forward, weighted CE, backward, NCCL all-reduce, Adam), batch 8
 per GPU at 1024^2; roofline = conv FLOPs of the step / whole step time; e2e = images + targets from pinned host memory,
 loss read back every step.

@@ -7,8 +7,10 @@ NeuralBarkCalculator.predict, models.py:173-203 and 230-364).
                      in flight so the PCIe link stays busy)
     writer threads : PNG encode of the processed image and of the 0/127/255 dual image (zlib releases the GIL)
 
-The files are the reference's (same names, same pixels, same CSV); only the PNG compression level is a knob
-(``png_compress_level``, pixels are unaffected).  Works for the standard input -- uncompressed 24-bit 4096x4096 BMP;
+The files are the reference's: same names, same CSV layout, and the pixels of the oracle's restatement of the reference --
+processed images equal to the reference's except, possibly, one LSB on exact rounding ties (the float -> u8 rounding of
+scikit-image 0.15's save path is unpinned, see oracle/preprocess.py), class maps within the floating-point bar of
+DESIGN.md 5.  Only the PNG compression level is a knob (``png_compress_level``, pixels are unaffected).  Works for the standard input -- uncompressed 24-bit 4096x4096 BMP;
 ``supported()`` says whether a folder qualifies, otherwise predict.py takes the per-image path of models.py."""
 import csv
 import os

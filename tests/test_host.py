@@ -382,3 +382,35 @@ def test_get_splits_and_epoch_sampler_match_reference(golden_dir):
     assert np.array_equal(tr2, tr) and np.array_equal(tw2, tw)
     b = nu.weighted_epoch_batches(tr, tw, 5, generator=torch.Generator().manual_seed(int(g['sampler_seed'])))
     assert np.array_equal(b.numpy(), g['batches'])
+
+
+def test_combined_image_modes(tmp_path, monkeypatch):
+    """results/combined_images: NBC_COMBINED selects the native stand-in (default), the reference's matplotlib figure
+    ('figure': an optional dependency -- loud error when it is missing, never a silent skip) or nothing."""
+    from PIL import Image
+    from neuralbarkcalculator_b200 import figure, pipeline
+    rng = np.random.default_rng(0)
+    proc = rng.integers(0, 255, (40, 64, 3), dtype=np.uint8)
+    mask = rng.integers(0, 3, (40, 64), dtype=np.uint8)
+    stats = ['12.50000', '1.00000', '0.25000', '2.00000']
+    monkeypatch.delenv('NBC_COMBINED', raising=False)
+    assert figure.mode() == 'standin'
+    out = str(tmp_path / 'c.png')
+    pipeline.write_combined(out, proc, mask, stats, 'a.png', [0.7, 0.6, 0.4], [0.1, 0.1, 0.1])
+    img = np.asarray(Image.open(out))
+    assert img.shape == (20 + 16, 2 * 32 + 8, 3) and np.array_equal(img[16:, :32], proc[::2, ::2])
+    monkeypatch.setenv('NBC_COMBINED', '0')
+    assert figure.mode() == 'off'
+    pipeline.write_combined(str(tmp_path / 'none.png'), proc, mask, stats, 'a.png', [0.7] * 3, [0.1] * 3)
+    assert not os.path.exists(str(tmp_path / 'none.png'))
+    monkeypatch.setenv('NBC_COMBINED', 'figure')
+    assert figure.mode() == 'figure'
+    assert figure.suptitle_text((12.5, 0.25)) == 'Estimated composition percentages\nBark : 12.500\nNode : 0.250\n'   # models.py:334-340
+    try:
+        import matplotlib  # noqa: F401
+    except ImportError:
+        with pytest.raises(RuntimeError, match='matplotlib'):
+            pipeline.write_combined(str(tmp_path / 'f.png'), proc, mask, stats, 'a.png', [0.7] * 3, [0.1] * 3)
+    else:
+        pipeline.write_combined(str(tmp_path / 'f.png'), proc, mask, stats, 'a.png', [0.7] * 3, [0.1] * 3)
+        assert os.path.getsize(str(tmp_path / 'f.png')) > 10000
