@@ -30,39 +30,55 @@ __global__ void __launch_bounds__(256) head1x1_kernel(const __nv_bfloat16* __res
     for (int k = 0; k < 3; ++k)
 #pragma unroll
       for (int e = 0; e < 8; ++e) wr[it][k][e] = __ldg(w + k * Cin + it * 256 + lane * 8 + e);
-  for (int64_t m = warp_global; m < M; m += nwarps) {
-    if (valid_h != nullptr) {      // ragged batch: rows at or below an image's last valid one feed nothing (K3 clamps its taps)
-      const int64_t img = m / P;
-      if ((m - img * P) / row_w >= __ldg(valid_h + img)) continue;
-    }
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    const __nv_bfloat16* xr = x + m * Cin + lane * 8;
-    uint4 v[kIters];
+  // kPix pixels per warp and iteration: their loads are all issued before the first FMA (one pixel at a time left the
+  // kernel at 1.5 TB/s -- too little memory-level parallelism)
+  constexpr int kPix = 4;
+  for (int64_t m0 = warp_global; m0 < M; m0 += nwarps * kPix) {
+    uint4 v[kPix][kIters];
+    bool on[kPix];
 #pragma unroll
-    for (int it = 0; it < kIters; ++it) v[it] = __ldg(reinterpret_cast<const uint4*>(xr + it * 256));
+    for (int j = 0; j < kPix; ++j) {
+      const int64_t m = m0 + (int64_t)j * nwarps;
+      on[j] = m < M;
+      if (on[j] && valid_h != nullptr) {   // ragged batch: rows at or below an image's last valid one feed nothing (K3 clamps its taps)
+        const int64_t img = m / P;
+        on[j] = (m - img * P) / row_w < __ldg(valid_h + img);
+      }
+      if (on[j]) {
+        const __nv_bfloat16* xr = x + m * Cin + lane * 8;
 #pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-      const uint32_t u[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float f0 = lo16(u[k], f16), f1 = hi16(u[k], f16);
-        a0 = fmaf(f0, wr[it][0][2 * k], a0), a0 = fmaf(f1, wr[it][0][2 * k + 1], a0);
-        a1 = fmaf(f0, wr[it][1][2 * k], a1), a1 = fmaf(f1, wr[it][1][2 * k + 1], a1);
-        a2 = fmaf(f0, wr[it][2][2 * k], a2), a2 = fmaf(f1, wr[it][2][2 * k + 1], a2);
+        for (int it = 0; it < kIters; ++it) v[j][it] = __ldg(reinterpret_cast<const uint4*>(xr + it * 256));
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-    }
-    if (lane == 0) {
-      const int64_t img = m / P, pix = m - img * P;
-      float* o = logits + img * 3 * P + pix;
-      o[0] = a0 + b0;
-      o[P] = a1 + b1;
-      o[2 * P] = a2 + b2;
+    for (int j = 0; j < kPix; ++j) {
+      if (!on[j]) continue;      // warp-uniform
+      const int64_t m = m0 + (int64_t)j * nwarps;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int it = 0; it < kIters; ++it) {
+        const uint32_t u[4] = {v[j][it].x, v[j][it].y, v[j][it].z, v[j][it].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float f0 = lo16(u[k], f16), f1 = hi16(u[k], f16);
+          a0 = fmaf(f0, wr[it][0][2 * k], a0), a0 = fmaf(f1, wr[it][0][2 * k + 1], a0);
+          a1 = fmaf(f0, wr[it][1][2 * k], a1), a1 = fmaf(f1, wr[it][1][2 * k + 1], a1);
+          a2 = fmaf(f0, wr[it][2][2 * k], a2), a2 = fmaf(f1, wr[it][2][2 * k + 1], a2);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+      }
+      if (lane == 0) {
+        const int64_t img = m / P, pix = m - img * P;
+        float* o = logits + img * 3 * P + pix;
+        o[0] = a0 + b0;
+        o[P] = a1 + b1;
+        o[2 * P] = a2 + b2;
+      }
     }
   }
 }

@@ -103,30 +103,28 @@ __global__ void __launch_bounds__(256) stem_kernel(const StemParams p) {
 template <bool kF32>
 __global__ void __launch_bounds__(256) stem_pad_kernel(const StemParams p, int Hp, int Wp, uint2* __restrict__ padded,
                                                        const int* __restrict__ valid_h) {
-  const int64_t total = (int64_t)p.N * Hp * Wp;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int x = (int)(i % Wp) - 3;
-    int64_t t = i / Wp;
-    const int y = (int)(t % Hp) - 3;
-    const int img = (int)(t / Hp);
-    float v[3] = {0.f, 0.f, 0.f};
-    const int vh = valid_h ? min(p.H, __ldg(valid_h + img)) : p.H;   // ragged batch: rows >= vh are zero padding
-    // ... of which the stem reads at most the 7-row window of its last valid output row (2 * ceil(vh / 2) + 3 < vh + 5);
-    // the dead part of the canvas below is never read and need not be written
-    if (valid_h && y >= vh + 8) continue;
-    if (y >= 0 && y < vh && x >= 0 && x < p.W) {
-      if (kF32) {
+  // grid (padded columns / 256, padded rows, images): plain 32-bit index arithmetic (the first version's grid-stride loop
+  // spent its time in 64-bit divisions)
+  const int xp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xp >= Wp) return;
+  const int x = xp - 3, y = (int)blockIdx.y - 3, img = blockIdx.z;
+  const int vh = valid_h ? min(p.H, __ldg(valid_h + img)) : p.H;   // ragged batch: rows >= vh are zero padding
+  // ... of which the stem reads at most the 7-row window of its last valid output row (2 * ceil(vh / 2) + 3 < vh + 5);
+  // the dead part of the canvas below is never read and need not be written
+  if (valid_h && y >= vh + 8) return;
+  float v[3] = {0.f, 0.f, 0.f};
+  if (y >= 0 && y < vh && x >= 0 && x < p.W) {
+    if (kF32) {
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) v[ch] = __ldg(p.xf + (((int64_t)img * 3 + ch) * p.H + y) * p.W + x);
-      } else {
-        const uint8_t* s = p.img + (((int64_t)img * p.H + y) * p.W + x) * 3;
+      for (int ch = 0; ch < 3; ++ch) v[ch] = __ldg(p.xf + (((int64_t)img * 3 + ch) * p.H + y) * p.W + x);
+    } else {
+      const uint8_t* s = p.img + (((int64_t)img * p.H + y) * p.W + x) * 3;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch)
-          v[ch] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)s[ch], 255.f), p.mean[ch]), p.std[ch]);
-      }
+      for (int ch = 0; ch < 3; ++ch)
+        v[ch] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)s[ch], 255.f), p.mean[ch]), p.std[ch]);
     }
-    padded[i] = make_uint2(pack16x2(v[0], v[1], p.f16), pack16x2(v[2], 0.f, p.f16));
   }
+  padded[((int64_t)img * Hp + blockIdx.y) * Wp + xp] = make_uint2(pack16x2(v[0], v[1], p.f16), pack16x2(v[2], 0.f, p.f16));
 }
 
 // stem weights f32 [64][7][7][3] (BN folded) -> bf16 [64][7][8][4], zero for kx == 7 or c == 3  (K = 224)
@@ -139,47 +137,46 @@ __global__ void stem_pack_kernel(const float* __restrict__ w, unsigned short* __
   out[i] = cvt16(v, f16);
 }
 
-// maxpool 3x3 stride 2 pad 1 (padding = -inf), bf16 NHWC, 8 channels per thread
+// maxpool 3x3 stride 2 pad 1 (padding = -inf), 16-bit NHWC, 8 channels per thread; grid (Wo * C/8 / 256, Ho, N).  The
+// maximum is taken on the packed 16-bit pairs (HMNMX2): the result is one of the stored values, bit for bit.
+__device__ __forceinline__ uint32_t max16x2(uint32_t a, uint32_t b, int f16) {
+  if (f16) {
+    const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C,
                                                       int Ho, int Wo, __nv_bfloat16* __restrict__ y,
                                                       const int* __restrict__ valid_h, int f16) {
   const int cg = C >> 3;
-  const int64_t total = (int64_t)N * Ho * Wo * cg;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % cg);
-    int64_t t = i / cg;
-    const int wo = (int)(t % Wo);
-    t /= Wo;
-    const int ho = (int)(t % Ho);
-    const int n = (int)(t / Ho);
-    if (valid_h != nullptr) {   // ragged batch: zero halo rows after the valid ones, nothing beyond
-      const int vh = __ldg(valid_h + n);
-      if (ho >= vh) {
-        if (ho < vh + 4) *reinterpret_cast<uint4*>(y + (((int64_t)n * Ho + ho) * Wo + wo) * C + c8 * 8) = make_uint4(0, 0, 0, 0);
-        continue;
-      }
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Wo * cg) return;
+  const int c8 = t % cg, wo = t / cg, ho = blockIdx.y, n = blockIdx.z;
+  uint4* dst = reinterpret_cast<uint4*>(y + (((int64_t)n * Ho + ho) * Wo + wo) * C + c8 * 8);
+  if (valid_h != nullptr) {   // ragged batch: zero halo rows after the valid ones, nothing beyond
+    const int vh = __ldg(valid_h + n);
+    if (ho >= vh) {
+      if (ho < vh + 4) *dst = make_uint4(0, 0, 0, 0);
+      return;
     }
-    float m[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
-#pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int h = 2 * ho + dy;
-      if (h < 0 || h >= H) continue;
-#pragma unroll
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int w = 2 * wo + dx;
-        if (w < 0 || w >= W) continue;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)n * H + h) * W + w) * C + c8 * 8));
-        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) m[2 * k] = fmaxf(m[2 * k], lo16(u[k], f16)), m[2 * k + 1] = fmaxf(m[2 * k + 1], hi16(u[k], f16));
-      }
-    }
-    // the maxima are values that were stored in this format: converting back is exact
-    *reinterpret_cast<uint4*>(y + (((int64_t)n * Ho + ho) * Wo + wo) * C + c8 * 8) =
-        make_uint4(pack16x2(m[0], m[1], f16), pack16x2(m[2], m[3], f16), pack16x2(m[4], m[5], f16), pack16x2(m[6], m[7], f16));
   }
+  const uint32_t neg_inf = f16 ? 0xFC00FC00u : 0xFF80FF80u;
+  uint32_t m[4] = {neg_inf, neg_inf, neg_inf, neg_inf};
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int h = 2 * ho + dy;
+    if (h < 0 || h >= H) continue;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int w = 2 * wo + dx;
+      if (w < 0 || w >= W) continue;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)n * H + h) * W + w) * C + c8 * 8));
+      m[0] = max16x2(m[0], v.x, f16), m[1] = max16x2(m[1], v.y, f16), m[2] = max16x2(m[2], v.z, f16), m[3] = max16x2(m[3], v.w, f16);
+    }
+  }
+  *dst = make_uint4(m[0], m[1], m[2], m[3]);
 }
 
 }  // namespace nbc
@@ -248,12 +245,12 @@ int stem_tc_pad(const void* input, int input_kind, int N, int H, int W, const fl
   p.N = N, p.H = H, p.W = W, p.Ho = (H - 1) / 2 + 1, p.Wo = (W - 1) / 2 + 1;
   for (int i = 0; i < 3; ++i) p.mean[i] = mean3 ? mean3[i] : 0.f, p.std[i] = std3 ? std3[i] : 1.f;
   const int Hp = 2 * p.Ho + 5, Wp = 2 * p.Wo + 6;
-  const int64_t total = (int64_t)N * Hp * Wp;
-  const int blocks = (int)(ceil_div64(total, 256) < 148 * 16 ? ceil_div64(total, 256) : 148 * 16);
+  NBC_REQUIRE(Hp <= 65535 && N <= 65535, "stem staging: image too tall / batch too large");
+  const dim3 grid(ceil_div(Wp, 256), Hp, N);
   if (input_kind == 1)
-    stem_pad_kernel<true><<<blocks, 256, 0, stream>>>(p, Hp, Wp, reinterpret_cast<uint2*>(padded), valid_h);
+    stem_pad_kernel<true><<<grid, 256, 0, stream>>>(p, Hp, Wp, reinterpret_cast<uint2*>(padded), valid_h);
   else
-    stem_pad_kernel<false><<<blocks, 256, 0, stream>>>(p, Hp, Wp, reinterpret_cast<uint2*>(padded), valid_h);
+    stem_pad_kernel<false><<<grid, 256, 0, stream>>>(p, Hp, Wp, reinterpret_cast<uint2*>(padded), valid_h);
   NBC_CHECK_LAUNCH();
   return 0;
 }
@@ -286,10 +283,10 @@ extern "C" int nbc_maxpool3x3s2_bf16(const void* x, int N, int H, int W, int C, 
   NBC_REQUIRE(x && y, "nbc_maxpool3x3s2_bf16: null pointer");
   NBC_REQUIRE(C % 8 == 0 && N > 0 && H > 0 && W > 0, "nbc_maxpool3x3s2_bf16: bad shape");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
-  const int blocks = (int)(ceil_div64(total, 256) < 148 * 16 ? ceil_div64(total, 256) : 148 * 16);
-  maxpool_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, Ho, Wo,
-                                             reinterpret_cast<__nv_bfloat16*>(y), nullptr, f16 ? 1 : 0);
+  NBC_REQUIRE(Ho <= 65535 && N <= 65535, "nbc_maxpool3x3s2_bf16: image too tall / batch too large");
+  maxpool_kernel<<<dim3(ceil_div(Wo * (C / 8), 256), Ho, N), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, Ho,
+                                                                              Wo, reinterpret_cast<__nv_bfloat16*>(y), nullptr,
+                                                                              f16 ? 1 : 0);
   NBC_CHECK_LAUNCH();
   return 0;
 }
@@ -297,10 +294,8 @@ extern "C" int nbc_maxpool3x3s2_bf16(const void* x, int N, int H, int W, int C, 
 namespace nbc {
 int maxpool_ragged(const void* x, int N, int H, int W, int C, void* y, const int* valid_h, cudaStream_t stream, int f16) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
-  const int blocks = (int)(ceil_div64(total, 256) < 148 * 16 ? ceil_div64(total, 256) : 148 * 16);
-  maxpool_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, Ho, Wo,
-                                             reinterpret_cast<__nv_bfloat16*>(y), valid_h, f16);
+  maxpool_kernel<<<dim3(ceil_div(Wo * (C / 8), 256), Ho, N), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, Ho,
+                                                                              Wo, reinterpret_cast<__nv_bfloat16*>(y), valid_h, f16);
   NBC_CHECK_LAUNCH();
   return 0;
 }
