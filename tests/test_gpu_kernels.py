@@ -480,6 +480,48 @@ def test_ccl_edge_cases(cuda_device):
     assert r is t and np.array_equal(t[0].cpu().numpy(), opost.remove_small_zones_2d(mm))
 
 
+def test_k3_k5_stay_inside_their_buffers(cuda_device):
+    """Bounds check of our own (compute-sanitizer is not available on the GPU pool): K3 and K5 work on views in the middle
+    of guard-filled buffers -- mask canvas, logits, workspace, counts -- sized EXACTLY as the ABI says; the guards must be
+    untouched afterwards and the dead rows of the ragged canvas (below each image's height) unwritten."""
+    ops = _ops()
+    from neuralbarkcalculator_b200 import _lib
+    lib = _lib.load()
+    dev = cuda_device
+    G = 4096
+    for (N, Hc, W, heights) in [(3, 96, 1024, [96, 41, 7]), (2, 50, 300, [50, 1]), (1, 33, 96, [20])]:
+        rng = np.random.default_rng(N)
+        hl = [(((h - 1) // 2 + 1 - 1) // 2 + 1 - 1) // 2 + 1 for h in heights]
+        hc, w = (((Hc - 1) // 2 + 1 - 1) // 2 + 1 - 1) // 2 + 1, (((W - 1) // 2 + 1 - 1) // 2 + 1 - 1) // 2 + 1
+
+        def guarded(nbytes, dtype):
+            raw = torch.full((nbytes + 2 * G,), 0xA5, dtype=torch.uint8, device=dev)
+            return raw, raw[G:G + nbytes].view(dtype)
+
+        raw_m, mask = guarded(N * Hc * W, torch.uint8)
+        mask = mask.view(N, Hc, W)
+        raw_l, logits = guarded(N * 3 * hc * w * 4, torch.float32)
+        logits = logits.view(N, 3, hc, w)
+        logits.copy_(torch.from_numpy(rng.standard_normal((N, 3, hc, w)).astype(np.float32)))
+        need = lib.nbc_ccl_workspace_bytes(N, Hc, W)
+        raw_w, ws = guarded(need, torch.uint8)
+        raw_c, counts = guarded(N * 3 * 4, torch.int32)
+        counts = counts.view(N, 3)
+        hd = torch.tensor(heights, dtype=torch.int32, device=dev)
+        ops.upsample_argmax_ragged(logits, hd, (Hc, W), out=mask)
+        ops.remove_small_zones_ragged(mask, hd, 150, True, workspace=ws, counts=counts)
+        torch.cuda.synchronize()
+        for name, raw, n in (('mask', raw_m, N * Hc * W), ('logits', raw_l, N * 3 * hc * w * 4), ('workspace', raw_w, need),
+                             ('counts', raw_c, N * 12)):
+            assert bool((raw[:G] == 0xA5).all()) and bool((raw[G + n:] == 0xA5).all()), '%s guard overwritten (%s)' % (name, (N, Hc, W))
+        for i, h in enumerate(heights):
+            assert bool((mask[i, h:] == 0xA5).all()), 'dead rows of image %d written' % i
+            assert int(counts[i].sum()) == h * W
+            up = omodel.upsample_bicubic_restated(logits[i:i + 1, :, :hl[i]].cpu().numpy(), (h, W))
+            exp = opost.exclude_nodes(opost.remove_small_zones_2d(omodel.argmax_lowest(up)[0]))
+            assert np.array_equal(mask[i, :h].cpu().numpy(), exp), (N, Hc, W, i)
+
+
 def test_ccl_idempotent_full_size(cuda_device):
     ops = _ops()
     m = torch.from_numpy(np.stack([synth.class_mask(1024, 1024, 77 + i) for i in range(4)])).to(cuda_device)
