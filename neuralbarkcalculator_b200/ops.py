@@ -114,7 +114,8 @@ def preprocess_4x_batch(raws, H, W, spans=None, pitch=None, bgr=False, bottom_up
 def preprocess_general(raw, H, W, target=1024, pitch=None, bgr=False, bottom_up=False):
     """General-ratio variant of ``preprocess_4x``: any H x W pixel array -> target x target cubic resize + trim
     (models.py:194-203).  Returns (out u8 [target*target*3] flat buffer, first_last int32[2] CUDA tensor); the trimmed
-    image is ``out[:(last-first)*target*3].view(last-first, target, 3)``.  EXPERIMENTAL (see include/nbc.h)."""
+    image is ``out[:(last-first)*target*3].view(last-first, target, 3)``.  Byte-exact against oracle/preprocess.py::resize_general_f64
+    on B200 (tests/test_gpu_kernels.py::test_preprocess_general_ratio)."""
     lib = _lib.load()
     raw = _contig(raw, torch.uint8, 'raw')
     pitch = W * 3 if pitch is None else pitch
