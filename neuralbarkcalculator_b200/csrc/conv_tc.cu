@@ -107,12 +107,6 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvTcParams& p, int tile)
   t.h0 = th_i * p.th;
   return t;
 }
-// dead tile of a ragged batch: starts at or below the last valid row of its image -> no loads, no MMA
-__device__ __forceinline__ bool tile_dead(const ConvTcParams& p, int tile) {
-  if (p.valid_h == nullptr) return false;
-  const int mt = tile / p.num_n_tiles / p.tiles_w;
-  return (mt % p.tiles_h) * p.th >= __ldg(p.valid_h + mt / p.tiles_h);
-}
 // Ragged batches: the CTAs walk a COMPACT enumeration of the M tiles -- per image only the tiles that start above row
 // valid_h + kRaggedHalo (live tiles, then the few zero-halo tiles) -- so that the static round-robin over the persistent
 // CTAs stays balanced.  (Walking the dense numbering and skipping dead tiles left some CTAs with up to 20 % more live

@@ -436,7 +436,9 @@ def test_ccl_golden(cuda_device, golden_dir):
     assert counts[0].tolist() == np.bincount(g['out'].ravel(), minlength=3).tolist()
 
 
-@pytest.mark.parametrize('shape,thr', [((3, 200, 333), 150), ((1, 1024, 1024), 150), ((2, 611, 1024), 150), ((4, 64, 64), 9)])
+# (rows wider than 1024 pixels take the per-pixel kernels, everything else the run-based ones: both are covered)
+@pytest.mark.parametrize('shape,thr', [((3, 200, 333), 150), ((1, 1024, 1024), 150), ((2, 611, 1024), 150), ((4, 64, 64), 9),
+                                       ((2, 90, 1100), 150), ((1, 37, 1024), 30)])
 def test_ccl_random_vs_oracle(cuda_device, shape, thr):
     ops = _ops()
     N, H, W = shape
