@@ -24,9 +24,12 @@ import torch
 from . import ops
 
 
-# images per ragged batch: the per-launch cost of the 53 network kernels (launch gap, pipeline fill and drain, the last
-# partial wave) is amortised over the chunk -- 0.631 ms per image at 8, 0.608 at 12 (profiles/r01t_pdl_chunk_depth_sweep.txt)
-DEFAULT_CHUNK = 8
+# images per ragged batch.  Two effects, both measured (profiles/r02e_chunk_sweep.txt): the per-launch cost of the ~53 network
+# kernels (launch gap, pipeline fill and drain) is amortised over the chunk, and -- the larger one -- the last partial WAVE of
+# every conv launch: a chunk of 8 trimmed scans has ~620 M tiles at the 128-wide layers, i.e. 8.4 rounds of the 74 CTA pairs
+# (9 are paid), a chunk of 16 has 16.9 (17 are paid).  With K1 issued once per chunk the end-to-end path gains as well:
+# chunk 8 -> 16: value 1 395 -> 1 419 img/s, e2e 1 358 -> 1 397.
+DEFAULT_CHUNK = 16
 # raw-scan staging buffers of the host path (50 MB each), in units of chunks: K1 runs once per chunk (three launches for all
 # its scans), so the H2D stream needs a second chunk's worth of buffers to keep copying while K1 waits for its turn
 DEFAULT_STAGE_DEPTH = 2

@@ -2,7 +2,7 @@
 `ncu -i X.ncu-rep --page raw --csv`): one line per launch (duration, DRAM bytes, tensor-pipe activity) plus totals,
 and the small JSON bench.py reads for `roofline.traffic` / `tensor_pipe_active_pct_ncu`.
 
-usage: python tools/ncu_summarise.py RAW.csv OUT.txt [OUT.json] [--title "..."]"""
+usage: python tools/ncu_summarise.py RAW.csv OUT.txt [OUT.json] [--title "..."] [--shape "[16,624,1024,3]"]"""
 import csv
 import json
 import sys
@@ -15,6 +15,9 @@ def main():
     title = sys.argv[sys.argv.index('--title') + 1] if '--title' in sys.argv else ''
     if '--title' in sys.argv:
         args.remove(title)
+    shape = sys.argv[sys.argv.index('--shape') + 1] if '--shape' in sys.argv else '[8,624,1024,3]'
+    if '--shape' in sys.argv:
+        args.remove(shape)
     raw, out_txt = args[0], args[1]
     out_json = args[2] if len(args) > 2 else None
     rows = list(csv.reader(open(raw)))
@@ -46,8 +49,7 @@ def main():
                 'active %.1f %%\n' % (n, tot_us / 1e3, tot_rd / 1e6, tot_wr / 1e6, (tot_rd + tot_wr) / n / 1e6, tw / tot_us))
     if out_json:
         json.dump({'conv_tc_dram_bytes_per_launch': (tot_rd + tot_wr) / n, 'launches': n,
-                   'workload': 'dense [8,624,1024,3] network pass (tools/prof_forward.py), %d conv_tc_kernel / '
-                               'conv_tc_pair_kernel launches' % n,
+                   'workload': 'dense %s network pass (tools/prof_forward.py), %d tensor-core conv launches' % (shape, n),
                    'dram_read_bytes_total': tot_rd, 'dram_write_bytes_total': tot_wr, 'ncu_time_ms_total': tot_us / 1e3,
                    'conv_tc_tensor_pipe_active_pct_time_weighted': tw / tot_us,
                    'source': out_txt + ' (ncu --set full, --clock-control none)'}, open(out_json, 'w'), indent=1)
