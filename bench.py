@@ -463,8 +463,8 @@ def main():
     roof = None
     cpu_base = None
     if rank == 0:
-        # The engine launches the network once per ragged chunk of 8 scans; the trimmed height of the synthetic scans
-        # averages 624 rows, so the representative launch is a dense [8,624,1024,3] batch (same tiles, same grid).
+        # The engine launches the network once per ragged chunk of scans (engine.DEFAULT_CHUNK); the trimmed height of the
+        # synthetic scans averages 624 rows, so the representative launch is a dense [chunk,624,1024,3] batch.
         from oracle import synth
         chunk = prof_n
         one = torch.from_numpy(synth.texture_u8(prof_h, 1024, 5)).unsqueeze(0).to(dev)
