@@ -13,6 +13,7 @@ scikit-image 0.15's save path is unpinned, see oracle/preprocess.py), class maps
 DESIGN.md 5.  Only the PNG compression level is a knob (``png_compress_level``, pixels are unaffected).  Works for the standard input -- uncompressed 24-bit 4096x4096 BMP;
 ``supported()`` says whether a folder qualifies, otherwise predict.py takes the per-image path of models.py."""
 import csv
+import mmap
 import os
 import struct
 import threading
@@ -126,6 +127,42 @@ def supported(items):
     return len(geo) > 0 and all(g is not None for g in geo) and len({g[1] for g in geo}) == 1
 
 
+def read_scan(path, off, buf, zero_span=True):
+    """Pixel array of a RAW x RAW 24-bit BMP (file offset ``off``) into the pinned buffer ``buf`` -> (row0, rows), the
+    memory rows between the scan's all-zero dark bands (whole groups of 4; engine.py).  With ``zero_span`` the file is
+    mapped, the bands are found in the page cache (``nbc_host_zero_row_span``: only the zero rows are touched) and ONLY the
+    rows in between are copied into ``buf`` -- the engine never reads the others; otherwise the whole array is read."""
+    nbytes, pitch = RAW * RAW * 3, RAW * 3
+    view = buf.numpy()
+    with open(path, 'rb', buffering=0) as f:
+        if zero_span:
+            try:
+                mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+            except (OSError, ValueError):
+                mm = None
+            if mm is not None:
+                try:
+                    if len(mm) < off + nbytes:
+                        raise IOError('short file: ' + path)
+                    src = np.frombuffer(mm, dtype=np.uint8, count=nbytes, offset=off)
+                    row0, rows = ops.host_zero_row_span(src, RAW, pitch)
+                    if rows:
+                        np.copyto(view[row0 * pitch:(row0 + rows) * pitch], src[row0 * pitch:(row0 + rows) * pitch])
+                    del src
+                finally:
+                    mm.close()
+                return row0, rows
+        f.seek(off)
+        mv = memoryview(view)
+        got = 0
+        while got < nbytes:
+            n = f.readinto(mv[got:nbytes])
+            if not n:
+                raise IOError('short read: ' + path)
+            got += n
+    return ops.host_zero_row_span(buf, RAW, pitch) if zero_span else (0, RAW)
+
+
 class FolderPipeline:
     def __init__(self, calculator, batch=16, io_threads=None, png_compress_level=None):
         if png_compress_level is None:      # 0 = stored (fastest, 1.9 MB per processed image), 1 = fast deflate (default)
@@ -138,17 +175,6 @@ class FolderPipeline:
         self.io_threads = io_threads or max(4, min(32, (os.cpu_count() or 8)))
         self.png_level = png_compress_level
         self.engine = PredictEngine(calculator.model, calculator.device, raw_size=RAW)
-
-    def _read_into(self, path, off, buf):
-        with open(path, 'rb', buffering=0) as f:
-            f.seek(off)
-            view = memoryview(buf.numpy())
-            got = 0
-            while got < len(view):
-                n = f.readinto(view[got:])
-                if not n:
-                    raise IOError('short read: ' + path)
-                got += n
 
     def run(self, root_path, excludes_nodes, only_preprocess=False, shard=None):
         """shard=(start, end): process only that slice of the dataset order and return its CSV rows WITHOUT writing
@@ -188,9 +214,9 @@ class FolderPipeline:
             if pinned[tok] is None:
                 pinned[tok] = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
             t0 = time.perf_counter()
-            self._read_into(items[i][0], geo[i][0], pinned[tok])
-            # the reader knows the scan best while it is cache-hot: the all-zero dark bands stay on the host (engine.py)
-            spans[tok] = ops.host_zero_row_span(pinned[tok], RAW, RAW * 3) if self.engine.zero_span else (0, RAW)
+            # the reader finds the scan's all-zero dark bands while it reads: they never enter the pinned buffer, let alone
+            # cross PCIe (engine.py)
+            spans[tok] = read_scan(items[i][0], geo[i][0], pinned[tok], self.engine.zero_span)
             timing['read_s'] += time.perf_counter() - t0
             return tok
 

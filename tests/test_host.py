@@ -414,3 +414,29 @@ def test_combined_image_modes(tmp_path, monkeypatch):
     else:
         pipeline.write_combined(str(tmp_path / 'f.png'), proc, mask, stats, 'a.png', [0.7] * 3, [0.1] * 3)
         assert os.path.getsize(str(tmp_path / 'f.png')) > 10000
+
+
+def test_read_scan_copies_only_the_rows_between_the_dark_bands(tmp_path):
+    """pipeline.read_scan (host code): a 4096^2 BMP is mapped, its all-zero bands are found in the page cache and only the
+    span in between lands in the (pinned) buffer; the span equals nbc_host_zero_row_span of the whole array, and the
+    plain-read path gives the same span with the whole array copied."""
+    from neuralbarkcalculator_b200 import pipeline
+    from oracle import synth
+    RAW = pipeline.RAW
+    rng = np.random.default_rng(0)
+    img = np.zeros((RAW, RAW, 3), np.uint8)
+    img[1201:2999] = rng.integers(1, 255, (1798, RAW, 3), dtype=np.uint8)     # band edges that are not multiples of 4
+    path = str(tmp_path / 'scan.bmp')
+    synth.write_bmp(path, img)
+    off, bottom_up = pipeline.bmp_geometry(path)
+    pitch = RAW * 3
+    buf = torch.full((RAW * RAW * 3,), 0x5A, dtype=torch.uint8)
+    row0, rows = pipeline.read_scan(path, off, buf, True)
+    whole = torch.empty(RAW * RAW * 3, dtype=torch.uint8)
+    assert pipeline.read_scan(path, off, whole, False) == (0, RAW)
+    from neuralbarkcalculator_b200 import ops
+    assert (row0, rows) == ops.host_zero_row_span(whole, RAW, pitch)
+    assert row0 % 4 == 0 and rows % 4 == 0 and 0 < rows < RAW
+    assert torch.equal(buf[row0 * pitch:(row0 + rows) * pitch], whole[row0 * pitch:(row0 + rows) * pitch])
+    assert bool((buf[:row0 * pitch] == 0x5A).all()) and bool((buf[(row0 + rows) * pitch:] == 0x5A).all())      # never written
+    assert not whole[:row0 * pitch].any() and not whole[(row0 + rows) * pitch:].any()                          # ... and all zero
