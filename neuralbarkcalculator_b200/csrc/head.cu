@@ -14,14 +14,16 @@ namespace nbc {
 // kIters = Cin / 256: every lane owns 8 consecutive channels of each 256-channel slab and keeps its 3 x 8 x kIters
 // weights in registers, so the inner loop is one 16-byte load + 24 FMAs per slab.
 template <int kIters>
-__global__ void __launch_bounds__(256) head1x1_kernel(const __nv_bfloat16* __restrict__ x, int64_t P, int N, int Cin,
+__global__ void __launch_bounds__(256) head1x1_kernel(const __nv_bfloat16* __restrict__ x, int P, int N, int Cin,
                                                       const float* __restrict__ w, const float* __restrict__ bias,
                                                       float* __restrict__ logits, int f16, const int* __restrict__ valid_h,
                                                       int row_w) {
   const int lane = threadIdx.x & 31;
-  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t M = (int64_t)N * P;
+  // 32-bit pixel indices (the host checks N * P < 2^31): the first version's 64-bit divisions per pixel cost more than the
+  // 48 FMAs of the pixel
+  const int warp_global = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+  const int M = N * P;
   const float b0 = __ldg(bias), b1 = __ldg(bias + 1), b2 = __ldg(bias + 2);
   float wr[kIters][3][8];
 #pragma unroll
@@ -33,19 +35,19 @@ __global__ void __launch_bounds__(256) head1x1_kernel(const __nv_bfloat16* __res
   // kPix pixels per warp and iteration: their loads are all issued before the first FMA (one pixel at a time left the
   // kernel at 1.5 TB/s -- too little memory-level parallelism)
   constexpr int kPix = 4;
-  for (int64_t m0 = warp_global; m0 < M; m0 += nwarps * kPix) {
+  for (int m0 = warp_global; m0 < M; m0 += nwarps * kPix) {
     uint4 v[kPix][kIters];
     bool on[kPix];
 #pragma unroll
     for (int j = 0; j < kPix; ++j) {
-      const int64_t m = m0 + (int64_t)j * nwarps;
+      const int m = m0 + j * nwarps;
       on[j] = m < M;
       if (on[j] && valid_h != nullptr) {   // ragged batch: rows at or below an image's last valid one feed nothing (K3 clamps its taps)
-        const int64_t img = m / P;
+        const int img = m / P;
         on[j] = (m - img * P) / row_w < __ldg(valid_h + img);
       }
       if (on[j]) {
-        const __nv_bfloat16* xr = x + m * Cin + lane * 8;
+        const __nv_bfloat16* xr = x + (int64_t)m * Cin + lane * 8;
 #pragma unroll
         for (int it = 0; it < kIters; ++it) v[j][it] = __ldg(reinterpret_cast<const uint4*>(xr + it * 256));
       }
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(256) head1x1_kernel(const __nv_bfloat16* __res
 #pragma unroll
     for (int j = 0; j < kPix; ++j) {
       if (!on[j]) continue;      // warp-uniform
-      const int64_t m = m0 + (int64_t)j * nwarps;
+      const int m = m0 + j * nwarps;
       float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
       for (int it = 0; it < kIters; ++it) {
@@ -73,8 +75,8 @@ __global__ void __launch_bounds__(256) head1x1_kernel(const __nv_bfloat16* __res
         a2 += __shfl_xor_sync(0xffffffffu, a2, o);
       }
       if (lane == 0) {
-        const int64_t img = m / P, pix = m - img * P;
-        float* o = logits + img * 3 * P + pix;
+        const int img = m / P, pix = m - img * P;
+        float* o = logits + (int64_t)img * 3 * P + pix;
         o[0] = a0 + b0;
         o[P] = a1 + b1;
         o[2 * P] = a2 + b2;
@@ -235,15 +237,16 @@ int head_1x1(const void* x_bf16, int64_t pixels_per_image, int N, int Cin, const
   NBC_REQUIRE((Cin == 256 || Cin == 512 || Cin == 1024) && N > 0 && pixels_per_image > 0,
               "nbc_head_1x1: Cin must be 256, 512 or 1024 (got %d)", Cin);
   const int64_t M = (int64_t)N * pixels_per_image;
+  NBC_REQUIRE(M < (1ll << 31) - (1 << 24), "nbc_head_1x1: N * pixels_per_image must be < 2^31");
   const int64_t want = ceil_div64(M, 8 * 4);
   const int blocks = (int)(want < 148 * 8 ? (want < 1 ? 1 : want) : 148 * 8);
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x_bf16);
   if (Cin == 256)
-    head1x1_kernel<1><<<blocks, 256, 0, stream>>>(xb, pixels_per_image, N, Cin, w3xC, bias3, logits_planar, f16, valid_h, row_w);
+    head1x1_kernel<1><<<blocks, 256, 0, stream>>>(xb, (int)pixels_per_image, N, Cin, w3xC, bias3, logits_planar, f16, valid_h, row_w);
   else if (Cin == 512)
-    head1x1_kernel<2><<<blocks, 256, 0, stream>>>(xb, pixels_per_image, N, Cin, w3xC, bias3, logits_planar, f16, valid_h, row_w);
+    head1x1_kernel<2><<<blocks, 256, 0, stream>>>(xb, (int)pixels_per_image, N, Cin, w3xC, bias3, logits_planar, f16, valid_h, row_w);
   else
-    head1x1_kernel<4><<<blocks, 256, 0, stream>>>(xb, pixels_per_image, N, Cin, w3xC, bias3, logits_planar, f16, valid_h, row_w);
+    head1x1_kernel<4><<<blocks, 256, 0, stream>>>(xb, (int)pixels_per_image, N, Cin, w3xC, bias3, logits_planar, f16, valid_h, row_w);
   NBC_CHECK_LAUNCH();
   return 0;
 }
