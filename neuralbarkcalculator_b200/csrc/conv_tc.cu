@@ -1400,6 +1400,15 @@ static int build_launch(const ConvGeom& g, const void* x, const void* w, const f
     return (e && *e) ? atoi(e) : 0;
   }();
   if (residual != nullptr && res_bn == 128 && g.Cout % 128 == 0) bn = 128;
+  // experiment knob (NBC_SPLIT256=1): the Cout = 256 launches without a residual (layer3 conv1 / conv2) have ONE 256-column
+  // N tile, so their tile count is the number of M tiles -- ~620 pairs for a chunk of 16 scans = 8.4 rounds of the 74 CTA
+  // pairs, 9 paid.  Two 128-column N tiles (still on pairs) double the tile count: 16.9 rounds, 17 paid
+  static const int split256 = [] {
+    const char* e = getenv("NBC_SPLIT256");
+    return (e && *e) ? atoi(e) : 0;
+  }();
+  const bool split = split256 == 1 && residual == nullptr && g.Cout == 256 && g.kh * g.kw * (g.Cin / 64) >= 8;
+  if (split) bn = 128;
   L->block_n = bn;
   L->kblk = 64;
   p.num_n_tiles = g.Cout / bn;
@@ -1463,7 +1472,7 @@ static int build_launch(const ConvGeom& g, const void* x, const void* w, const f
                             (uint64_t)g.H * g.W * g.Cin * eb, kHaloW, 3);
     if (rc) return rc;
   }
-  L->pair = L->halo3 ? 0 : want_pair(residual != nullptr ? 2 : (p.n_taps > 1 ? 4 : 1), bn, p.n_taps * p.cblocks);
+  L->pair = L->halo3 ? 0 : (split ? 1 : want_pair(residual != nullptr ? 2 : (p.n_taps > 1 ? 4 : 1), bn, p.n_taps * p.cblocks));
   int rc = encode_weight_map(&p.tmB, w, (uint64_t)p.n_taps * g.Cin, g.Cout, L->pair ? bn / 2 : bn);
   if (rc) return rc;
   rc = encode_out_maps(&p, g.N, Ho, Wo, g.Cout, y, residual);
